@@ -1,0 +1,198 @@
+// acct_kernels.cu -- sm_100a device code of the gemhook accounting path.
+//
+// The reference hook has no device code at all: its only GPU-time measurement is one event pair per
+// token resolved on the host (reference Gemini/src/hook.cpp:456-502).  The B200-native hook stamps
+// launch segments with CUDA events (csrc/acct.cpp) and reduces the resulting 16-byte launch records
+// on the device, so the per-client running totals live next to the ring in HBM and only one small
+// snapshot per launch crosses to the mapped pinned totals page the host gate reads.
+//
+// Record (16 B, one uint4, see include/gemhook.h gemhook_record):
+//     x = slot            client slot in the credit pool; slot >= nslots is ignored
+//     y = launches        kernel launches covered by the record
+//     z,w = elapsed_ns    u64 little-endian: SM-time of the segment in nanoseconds
+// Output: per slot {sum elapsed_ns, sum launches, record count}, all u64 -> integer sums are
+// order-independent, so parity with the CPU oracle is bit-exact.
+//
+// Roofline: pure streaming read, 16 B per record, O(nslots) bytes written per block -> HBM-bound.
+// Design (see DESIGN.md "acct_reduce"):
+//   * every lane loads whole records with 128-bit ld.global.nc.L1::no_allocate (a warp covers
+//     512 contiguous bytes per load, UNROLL independent loads in flight per lane);
+//   * privatised accumulation without atomics: each warp owns a column-major bin table in shared
+//     memory, bins[slot][lane], so lane L only ever touches column L (conflict-free banks, no races);
+//   * block epilogue: columns are folded with __shfl_down_sync, warps are folded through shared
+//     memory, and ONE atomicAdd per (slot, field) per block goes to the device-resident totals;
+//   * the last block to finish (threadfence + ticket) publishes the running totals to the mapped
+//     pinned totals page with plain stores and bumps its sequence word (host side is a seqlock reader).
+//
+// Build: nvcc -cubin -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (csrc/Makefile); the cubin
+// is embedded in libgemhook.so.1 and loaded with cuModuleLoadData (no cudart dependency).
+
+#include <stdint.h>
+
+#define GEMHOOK_MAX_WARPS_PER_BLOCK 8  /* host picks 8 or 4 warps by shared-memory budget */
+#define GEMHOOK_UNROLL 8
+
+extern "C" {
+
+struct gemhook_totals_page {   // mapped pinned page (host reads it without any CUDA call)
+  unsigned long long seq;      // even = stable, odd = being written (seqlock)
+  unsigned long long epoch;    // number of reduce launches published
+  unsigned long long nslots;
+  unsigned long long reserved;
+  unsigned long long v[1];     // [nslots][3]: elapsed_ns, launches, records
+};
+
+__device__ __forceinline__ uint4 ld_stream_16(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// bins layout per warp: ns[nslots][32] u64 | la[nslots][32] u64 | rc[nslots][32] u32  (20 B per column cell)
+#define GEMHOOK_BIN_BYTES_PER_SLOT (32u * 20u)
+__device__ __forceinline__ void bin_add(unsigned long long* ns, unsigned long long* la, unsigned* rc,
+                                        unsigned nslots, unsigned lane, const uint4& r) {
+  if (r.x < nslots) {
+    unsigned idx = r.x * 32u + lane;
+    ns[idx] += ((unsigned long long)r.w << 32) | r.z;
+    la[idx] += r.y;
+    rc[idx] += 1u;
+  }
+}
+
+// dev_totals: [nslots][3] u64 running totals + 1 u64 publish counter (device memory, persistent)
+// ticket:     u32 zero-initialised, self-resetting
+__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32)
+gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigned nslots,
+                    unsigned long long* __restrict__ dev_totals, unsigned* __restrict__ ticket,
+                    gemhook_totals_page* __restrict__ page) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const unsigned nwarps = blockDim.x >> 5;
+  const unsigned per_warp_bytes = nslots * GEMHOOK_BIN_BYTES_PER_SLOT;
+  unsigned long long* ns = reinterpret_cast<unsigned long long*>(smem + warp * per_warp_bytes);
+  unsigned long long* la = ns + nslots * 32u;
+  unsigned* rc = reinterpret_cast<unsigned*>(la + nslots * 32u);
+
+  for (unsigned s = 0; s < nslots; s++) {
+    ns[s * 32u + lane] = 0ull;
+    la[s * 32u + lane] = 0ull;
+    rc[s * 32u + lane] = 0u;
+  }
+  __syncwarp();
+
+  // the per-column record count is u32: a lane sees at most n / (32 * warps) records, far below 2^32
+  // (the host splits reductions larger than 2^36 records, csrc/acct.cpp).
+  const unsigned long long warps_total = (unsigned long long)gridDim.x * nwarps;
+  const unsigned long long gwarp = (unsigned long long)blockIdx.x * nwarps + warp;
+  const unsigned long long tile = 32ull * GEMHOOK_UNROLL;  // records per warp-iteration
+  unsigned long long base = gwarp * tile;
+  const unsigned long long stride = warps_total * tile;
+
+  for (; base + tile <= n; base += stride) {
+    uint4 r[GEMHOOK_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GEMHOOK_UNROLL; u++) r[u] = ld_stream_16(rec + base + (unsigned)u * 32u + lane);
+#pragma unroll
+    for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add(ns, la, rc, nslots, lane, r[u]);
+  }
+  if (base < n) {  // ragged tail of this warp's last tile
+#pragma unroll 1
+    for (int u = 0; u < GEMHOOK_UNROLL; u++) {
+      unsigned long long i = base + (unsigned)u * 32u + lane;
+      if (i < n) {
+        uint4 r = ld_stream_16(rec + i);
+        bin_add(ns, la, rc, nslots, lane, r);
+      }
+    }
+  }
+  __syncwarp();
+
+  // fold the 32 columns of every slot with shuffles; lane 0 leaves the warp result in column 0
+  for (unsigned s = 0; s < nslots; s++) {
+    unsigned long long a = warp_sum_u64(ns[s * 32u + lane]);
+    unsigned long long l = warp_sum_u64(la[s * 32u + lane]);
+    unsigned long long k = warp_sum_u64((unsigned long long)rc[s * 32u + lane]);
+    __syncwarp();
+    if (lane == 0) {
+      ns[s * 32u] = a;
+      ns[s * 32u + 1] = l;
+      ns[s * 32u + 2] = k;
+    }
+  }
+  __syncthreads();
+
+  // fold warps: thread t handles (slot, field) = (t / 3, t % 3)
+  for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
+    unsigned s = t / 3u, f = t % 3u;
+    unsigned long long acc = 0ull;
+    for (unsigned w = 0; w < nwarps; w++) {
+      const unsigned long long* wns = reinterpret_cast<const unsigned long long*>(smem + w * per_warp_bytes);
+      acc += wns[s * 32u + f];
+    }
+    if (acc) atomicAdd(dev_totals + t, acc);
+  }
+
+  // last block publishes the running totals to the mapped pinned page
+  __shared__ unsigned is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicAdd(ticket, 1u);
+    is_last = (prev == gridDim.x - 1u) ? 1u : 0u;
+    if (is_last) *ticket = 0u;  // self-reset for the next launch (stream-ordered)
+  }
+  __syncthreads();
+  if (is_last && page) {
+    // dev_totals[nslots*3] is the device-resident publish counter: no read ever crosses PCIe
+    __shared__ unsigned long long e_sh;
+    __threadfence();
+    if (threadIdx.x == 0) {
+      unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(dev_totals + nslots * 3u) + 1ull;
+      e_sh = e;
+      *reinterpret_cast<volatile unsigned long long*>(&page->seq) = 2ull * e - 1ull;  // odd: writer active
+      __threadfence_system();
+    }
+    __syncthreads();
+    for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
+      // read through L2 (the atomics above were resolved there); volatile avoids a stale L1 line
+      page->v[t] = *reinterpret_cast<volatile unsigned long long*>(dev_totals + t);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long e = e_sh;
+      dev_totals[nslots * 3u] = e;
+      page->nslots = nslots;
+      page->epoch = e;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(&page->seq) = 2ull * e;
+    }
+  }
+}
+
+// Device-side timestamp record: one thread appends {slot, launches, globaltimer} -- used by the
+// stamp-kernel variant of segment marking (csrc/acct.cpp, GEMHOOK_STAMP=kernel) and by the bench's
+// primitive-cost probe.  kind: 0 = begin (subtract), 1 = end (add) -> totals += end - begin.
+__global__ void gemhook_stamp(unsigned long long* __restrict__ slot_ns_signed, unsigned slot, unsigned kind) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  if (kind) atomicAdd(slot_ns_signed + slot, t);
+  else atomicAdd(slot_ns_signed + slot, 0ull - t);
+}
+
+// Zero the running totals (stream-ordered reset).
+__global__ void gemhook_acct_clear(unsigned long long* __restrict__ dev_totals, unsigned n) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dev_totals[i] = 0ull;
+}
+
+}  // extern "C"

@@ -1,0 +1,284 @@
+// gh_acct.cpp -- host side of the device accounting path (include/gemhook.h section 2d).
+//
+// Owns: the embedded sm_100a cubin (acct_kernels.cu), a NON_BLOCKING accounting stream (so our work
+// never serialises with the application's legacy default stream), the device-resident record ring and
+// running totals, and the mapped pinned totals page.  Driver API only -- the hook must not drag a
+// second cudart into the application (the reference links cudart for five event calls, reference
+// hook.cpp:482-491, 543, 754).
+//
+// There is NO CPU fallback here: without a device (or with the wrong architecture) create() fails and
+// says why.
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "gh_internal.h"
+
+extern "C" {
+extern const unsigned char _binary_acct_kernels_cubin_start[];
+extern const unsigned char _binary_acct_kernels_cubin_end[];
+}
+
+namespace {
+
+struct totals_page {  // mirrors gemhook_totals_page in acct_kernels.cu
+  volatile uint64_t seq;
+  volatile uint64_t epoch;
+  volatile uint64_t nslots;
+  uint64_t reserved;
+  volatile uint64_t v[GEMHOOK_MAX_SLOTS * 3];
+};
+
+const unsigned BIN_BYTES_PER_SLOT = 32u * 20u;  // GEMHOOK_BIN_BYTES_PER_SLOT
+const unsigned TILE_RECORDS = 32u * 8u;         // records per warp iteration (32 lanes x GEMHOOK_UNROLL)
+
+const char* cu_err(CUresult r) {
+  const char* s = nullptr;
+  if (gh_real.cuGetErrorString) GH_CALL(cuGetErrorString, r, &s);
+  return s ? s : "unknown CUDA error";
+}
+
+}  // namespace
+
+#define CU_TRY(expr)                                                             \
+  do {                                                                           \
+    CUresult _r = (expr);                                                        \
+    if (_r != CUDA_SUCCESS) {                                                    \
+      gh_set_error("%s failed: %d (%s) at %s:%d", #expr, (int)_r, cu_err(_r), __FILE__, __LINE__); \
+      return -1;                                                                 \
+    }                                                                            \
+  } while (0)
+
+struct gemhook_acct {
+  CUcontext ctx = nullptr;
+  CUmodule mod = nullptr;
+  CUfunction f_reduce = nullptr, f_clear = nullptr, f_stamp = nullptr;
+  CUstream stream = nullptr;
+  CUevent ev0 = nullptr, ev1 = nullptr;
+  CUdeviceptr d_ring = 0, d_totals = 0, d_ticket = 0, d_page = 0;
+  totals_page* page = nullptr;
+  size_t ring_cap = 0;
+  uint32_t nslots = 0;
+  unsigned warps = 8, smem_bytes = 0, max_blocks = 0;
+  int sm_count = 0;
+  std::atomic<uint64_t> kernel_launches{0};
+  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+};
+
+static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
+  if (gh_driver_init() != 0) return -1;
+  if (nslots == 0 || nslots > GEMHOOK_MAX_SLOTS) {
+    gh_set_error("nslots %u out of range 1..%d", nslots, GEMHOOK_MAX_SLOTS);
+    return -1;
+  }
+  CU_TRY(GH_CALL(cuCtxGetCurrent, &a->ctx));
+  if (!a->ctx) {
+    gh_set_error("no CUDA context is current on the calling thread");
+    return -1;
+  }
+  CUdevice dev;
+  CU_TRY(GH_CALL(cuCtxGetDevice, &dev));
+  int major = 0, minor = 0;
+  CU_TRY(GH_CALL(cuDeviceGetAttribute, &major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, dev));
+  CU_TRY(GH_CALL(cuDeviceGetAttribute, &minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, dev));
+  CU_TRY(GH_CALL(cuDeviceGetAttribute, &a->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+  if (major != 10) {
+    gh_set_error("accounting kernels are built for sm_100a only; device is sm_%d%d", major, minor);
+    return -1;
+  }
+  CU_TRY(GH_CALL(cuModuleLoadData, &a->mod, (const void*)_binary_acct_kernels_cubin_start));
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, "gemhook_acct_reduce"));
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_clear, a->mod, "gemhook_acct_clear"));
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_stamp, a->mod, "gemhook_stamp"));
+  CU_TRY(GH_CALL(cuStreamCreate, &a->stream, CU_STREAM_NON_BLOCKING));
+  CU_TRY(GH_CALL(cuEventCreate, &a->ev0, CU_EVENT_DEFAULT));
+  CU_TRY(GH_CALL(cuEventCreate, &a->ev1, CU_EVENT_DEFAULT));
+
+  a->nslots = nslots;
+  // privatised bins: warps x nslots x 640 B of shared memory per block; keep >= 2 blocks per SM when possible
+  a->warps = (8u * nslots * BIN_BYTES_PER_SLOT <= 100u * 1024u) ? 8u : 4u;
+  a->smem_bytes = a->warps * nslots * BIN_BYTES_PER_SLOT;
+  if (a->smem_bytes > 48u * 1024u)
+    CU_TRY(GH_CALL(cuFuncSetAttribute, a->f_reduce, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)a->smem_bytes));
+  int per_sm = 0;
+  CU_TRY(GH_CALL(cuOccupancyMaxActiveBlocksPerMultiprocessor, &per_sm, a->f_reduce, (int)(a->warps * 32u),
+                 (size_t)a->smem_bytes));
+  if (per_sm < 1) per_sm = 1;
+  a->max_blocks = (unsigned)(per_sm * a->sm_count);  // one full wave: a multiple of the SM count
+
+  a->ring_cap = ring_cap ? ring_cap : (1u << 16);
+  CU_TRY(GH_CALL(cuMemAlloc_v2, &a->d_ring, a->ring_cap * sizeof(gemhook_record)));
+  size_t tot_bytes = ((size_t)nslots * 3 + 1) * sizeof(uint64_t);
+  CU_TRY(GH_CALL(cuMemAlloc_v2, &a->d_totals, tot_bytes));
+  CU_TRY(GH_CALL(cuMemAlloc_v2, &a->d_ticket, 256));
+  CU_TRY(GH_CALL(cuMemsetD8Async, a->d_totals, 0, tot_bytes, a->stream));
+  CU_TRY(GH_CALL(cuMemsetD8Async, a->d_ticket, 0, 256, a->stream));
+  void* hp = nullptr;
+  CU_TRY(GH_CALL(cuMemHostAlloc, &hp, sizeof(totals_page), CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+  memset(hp, 0, sizeof(totals_page));
+  a->page = (totals_page*)hp;
+  CU_TRY(GH_CALL(cuMemHostGetDevicePointer_v2, &a->d_page, hp, 0));
+  CU_TRY(GH_CALL(cuStreamSynchronize, a->stream));
+  GH_INFO("acct: %d SMs, nslots %u, %u warps/block, %u B smem, wave %u blocks", a->sm_count, nslots, a->warps,
+          a->smem_bytes, a->max_blocks);
+  return 0;
+}
+
+GH_EXPORT gemhook_acct* gemhook_acct_create(uint32_t nslots, size_t ring_capacity_records) {
+  gemhook_acct* a = new gemhook_acct();
+  if (acct_init(a, nslots, ring_capacity_records) != 0) {
+    gemhook_acct_destroy(a);
+    return nullptr;
+  }
+  return a;
+}
+
+GH_EXPORT void gemhook_acct_destroy(gemhook_acct* a) {
+  if (!a) return;
+  if (a->stream) GH_CALL(cuStreamSynchronize, a->stream);
+  if (a->d_ring) GH_CALL(cuMemFree_v2, a->d_ring);
+  if (a->d_totals) GH_CALL(cuMemFree_v2, a->d_totals);
+  if (a->d_ticket) GH_CALL(cuMemFree_v2, a->d_ticket);
+  if (a->page) GH_CALL(cuMemFreeHost, (void*)a->page);
+  if (a->ev0) GH_CALL(cuEventDestroy_v2, a->ev0);
+  if (a->ev1) GH_CALL(cuEventDestroy_v2, a->ev1);
+  if (a->stream) GH_CALL(cuStreamDestroy_v2, a->stream);
+  if (a->mod) GH_CALL(cuModuleUnload, a->mod);
+  delete a;
+}
+
+GH_EXPORT uint32_t gemhook_acct_grid_for(const gemhook_acct* a, size_t n) {
+  size_t per_block = (size_t)a->warps * TILE_RECORDS;
+  size_t want = (n + per_block - 1) / per_block;
+  if (want < 1) want = 1;
+  if (want > a->max_blocks) want = a->max_blocks;
+  return (uint32_t)want;
+}
+
+// launch the reduction over n records at device address d_rec (stream-ordered, no host sync)
+static int launch_reduce(gemhook_acct* a, CUdeviceptr d_rec, size_t n) {
+  unsigned long long nn = n;
+  unsigned ns = a->nslots;
+  void* args[] = {&d_rec, &nn, &ns, &a->d_totals, &a->d_ticket, &a->d_page};
+  unsigned grid = gemhook_acct_grid_for(a, n);
+  CU_TRY(GH_CALL(cuLaunchKernel, a->f_reduce, grid, 1, 1, a->warps * 32u, 1, 1, a->smem_bytes, a->stream, args,
+                 nullptr));
+  a->kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+GH_EXPORT int gemhook_acct_reduce_device(gemhook_acct* a, uint64_t d_records, size_t n, float* kernel_ms_out) {
+  if (!a) return -1;
+  if (d_records & 15u) {
+    gh_set_error("records must be 16-byte aligned");
+    return -1;
+  }
+  pthread_mutex_lock(&a->mu);
+  int rc = 0;
+  if (kernel_ms_out) rc = (GH_CALL(cuEventRecord, a->ev0, a->stream) == CUDA_SUCCESS) ? 0 : -1;
+  if (rc == 0 && n) rc = launch_reduce(a, (CUdeviceptr)d_records, n);
+  if (rc == 0 && kernel_ms_out) {
+    if (GH_CALL(cuEventRecord, a->ev1, a->stream) != CUDA_SUCCESS || GH_CALL(cuEventSynchronize, a->ev1) != CUDA_SUCCESS ||
+        GH_CALL(cuEventElapsedTime, kernel_ms_out, a->ev0, a->ev1) != CUDA_SUCCESS) {
+      gh_set_error("event timing of the reduce kernel failed");
+      rc = -1;
+    }
+  }
+  pthread_mutex_unlock(&a->mu);
+  return rc;
+}
+
+static int read_page(gemhook_acct* a, uint64_t* totals_out, uint64_t* epoch_out) {
+  // seqlock reader over the mapped pinned page: retry while the device is mid-publish
+  for (int tries = 0; tries < 1000000; tries++) {
+    uint64_t s0 = a->page->seq;
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    if (s0 & 1u) continue;
+    uint64_t ep = a->page->epoch;
+    if (totals_out)
+      for (uint32_t i = 0; i < a->nslots * 3; i++) totals_out[i] = a->page->v[i];
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    if (a->page->seq == s0) {
+      if (epoch_out) *epoch_out = ep;
+      return 0;
+    }
+  }
+  gh_set_error("totals page never became stable");
+  return -1;
+}
+
+GH_EXPORT int gemhook_acct_read_totals(gemhook_acct* a, uint64_t* totals_out, uint64_t* epoch_out) {
+  if (!a) return -1;
+  return read_page(a, totals_out, epoch_out);
+}
+
+GH_EXPORT int gemhook_acct_reduce_host(gemhook_acct* a, const gemhook_record* records, size_t n, uint64_t* totals_out) {
+  if (!a) return -1;
+  pthread_mutex_lock(&a->mu);
+  int rc = 0;
+  size_t done = 0;
+  while (done < n && rc == 0) {
+    size_t chunk = n - done < a->ring_cap ? n - done : a->ring_cap;
+    // stream order makes the ring safe to reuse: copy k+1 cannot start before kernel k finished
+    if (GH_CALL(cuMemcpyHtoDAsync_v2, a->d_ring, records + done, chunk * sizeof(gemhook_record), a->stream) != CUDA_SUCCESS) {
+      gh_set_error("H2D copy of %zu records failed", chunk);
+      rc = -1;
+      break;
+    }
+    rc = launch_reduce(a, a->d_ring, chunk);
+    done += chunk;
+  }
+  if (rc == 0 && GH_CALL(cuStreamSynchronize, a->stream) != CUDA_SUCCESS) {
+    gh_set_error("accounting stream failed");
+    rc = -1;
+  }
+  if (rc == 0 && totals_out) {
+    if (n == 0 && a->page->epoch == 0) memset(totals_out, 0, sizeof(uint64_t) * a->nslots * 3);
+    else rc = read_page(a, totals_out, nullptr);
+  }
+  pthread_mutex_unlock(&a->mu);
+  return rc;
+}
+
+GH_EXPORT int gemhook_acct_sync(gemhook_acct* a) {
+  if (!a) return -1;
+  CU_TRY(GH_CALL(cuStreamSynchronize, a->stream));
+  return 0;
+}
+
+GH_EXPORT int gemhook_acct_reset(gemhook_acct* a) {
+  if (!a) return -1;
+  pthread_mutex_lock(&a->mu);
+  unsigned cnt = a->nslots * 3;  // the publish counter (last word) keeps counting
+  void* args[] = {&a->d_totals, &cnt};
+  CUresult r = GH_CALL(cuLaunchKernel, a->f_clear, 1, 1, 1, 256, 1, 1, 0, a->stream, args, nullptr);
+  if (r == CUDA_SUCCESS) a->kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  if (r == CUDA_SUCCESS) r = GH_CALL(cuStreamSynchronize, a->stream);
+  for (uint32_t i = 0; i < a->nslots * 3; i++) a->page->v[i] = 0;
+  pthread_mutex_unlock(&a->mu);
+  if (r != CUDA_SUCCESS) {
+    gh_set_error("reset failed: %d", (int)r);
+    return -1;
+  }
+  return 0;
+}
+
+GH_EXPORT uint64_t gemhook_acct_kernel_launches(const gemhook_acct* a) {
+  return a ? a->kernel_launches.load(std::memory_order_relaxed) : 0;
+}
+GH_EXPORT uint64_t gemhook_acct_stream(const gemhook_acct* a) { return a ? (uint64_t)(uintptr_t)a->stream : 0; }
+
+// internal helpers for the live hook (gh_hook.cpp)
+int gh_acct_push_async(gemhook_acct* a, const gemhook_record* pinned_records, size_t n) {
+  // records live in pinned host memory owned by the caller and stay valid until the next sync
+  pthread_mutex_lock(&a->mu);
+  int rc = 0;
+  if (n > a->ring_cap) n = a->ring_cap;
+  if (GH_CALL(cuMemcpyHtoDAsync_v2, a->d_ring, pinned_records, n * sizeof(gemhook_record), a->stream) != CUDA_SUCCESS) rc = -1;
+  if (rc == 0) rc = launch_reduce(a, a->d_ring, n);
+  pthread_mutex_unlock(&a->mu);
+  return rc;
+}

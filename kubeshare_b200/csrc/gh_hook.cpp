@@ -1,0 +1,532 @@
+// gh_hook.cpp -- the live hook: process singleton, launch slow path, token renewal, overuse tracker,
+// segment accounting.  The per-launch FAST path is in gh_interpose.cpp: one load of gh_gate_open and one
+// relaxed increment -- no mutex, no clock read, no syscall (the reference takes three mutex pairs per
+// launch: window.record_stop, expiration_status_mutex, burst.record_start; hook.cpp:515-555).
+//
+// Reference behaviour kept (hook.cpp): first-use initialisation incl. a discarded first token (:724-771);
+// renewal only at a burst edge when `held + predicted_burst >= quota` (:520-521); the GPU is drained and
+// overuse measured with ONE event pair per token before a new token is requested (:456-502, 527-538);
+// sync calls end the burst and start a window (:334-340).
+//
+// New: (a) every burst (and optionally every K launches inside it) is bracketed by CUDA events on the
+// launching stream; the (slot, launches, elapsed_ns) records are reduced ON THE DEVICE by the sm_100a
+// kernel on a dedicated non-blocking accounting stream and published to a mapped pinned page;
+// (b) gpu_mem is enforced against the shared pool counter; (c) tokens come from the shared credit pool
+// when GEMHOOK_POOL is set (TCP to the unmodified gem-pmgr/gem-schd otherwise).
+#include <errno.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <atomic>
+
+#include "gh_internal.h"
+
+int gh_rpc(gemhook_request* req, gemhook_response* rsp);
+int gh_acct_push_async(gemhook_acct* a, const gemhook_record* pinned_records, size_t n);
+void gh_pool_publish_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches);
+void* gh_pool_region(gemhook_pool* p, size_t* bytes);
+
+volatile uint32_t gh_gate_open = 0;
+uint64_t gh_launch_count = 0;
+uint32_t gh_seg_mask = 0xffffffffu;
+
+namespace {
+const int SEG_EVENTS = 64;
+}
+
+struct gh_live {
+  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;  // guards gate + segments (expiration_status_mutex's role)
+  pthread_cond_t renew_cv = PTHREAD_COND_INITIALIZER;
+  bool renewing = false;
+  gemhook_gate* gate = nullptr;
+  bool enabled = false;
+  bool cuda_ready = false;
+
+  // transport
+  gemhook_pool* pool = nullptr;
+  int slot = 0;
+
+  // CUDA objects
+  CUcontext ctx = nullptr;
+  CUevent ev_token = nullptr, ev_drain = nullptr;
+  gemhook_acct* acct = nullptr;
+
+  // overuse tracker (hook.cpp:456-502)
+  pthread_t trk_tid;
+  pthread_mutex_t trk_mu = PTHREAD_MUTEX_INITIALIZER;
+  pthread_cond_t trk_start_cv = PTHREAD_COND_INITIALIZER, trk_done_cv = PTHREAD_COND_INITIALIZER;
+  pthread_cond_t trk_intr_cv;  // CLOCK_MONOTONIC
+  bool trk_armed = false, trk_done = true, trk_intr = false;
+  int64_t trk_deadline_ns = 0;
+
+  // segments: events bracketing launch runs on the launching stream
+  CUevent seg_ev[SEG_EVENTS];
+  int seg_head = 0;      // index of the event that opened the current segment (-1: none open)
+  bool seg_open = false;
+  CUstream seg_stream = nullptr;
+  uint64_t seg_first_launch = 0;
+  struct Pending {
+    int ev_begin, ev_end;
+    uint32_t launches;
+  } pending[SEG_EVENTS];
+  int npending = 0;
+  bool seg_end_recorded = false;
+
+  // staging of records (pinned, double buffered)
+  gemhook_record* stage[2] = {nullptr, nullptr};
+  uint32_t stage_cap = 0, stage_n = 0;
+  int stage_cur = 0;
+
+  // stats
+  std::atomic<uint64_t> slow_path{0}, token_requests{0}, host_syncs{0}, segments{0};
+  uint64_t gpu_ns_host = 0;  // host-side running sum of the same records (cross-check of the device totals)
+  double token_wait_ms = 0, accumulated_token_ms = 0;
+  int64_t last_token_ns = 0;
+  double last_quota_ms = 0;
+};
+
+static gh_live* g_live = nullptr;
+static pthread_once_t live_once = PTHREAD_ONCE_INIT;
+
+static void fatal_or_disable(gh_live* L, const char* what) {
+  gh_set_error("%s", what);
+  fprintf(stderr, "[gemhook %d] %s\n", (int)getpid(), what);
+  if (gh_cfg.exit_on_failure) exit(1);  // reference: exit() of the application (hook.cpp:236, 285, 360, 388, 439)
+  L->enabled = false;
+}
+
+// ---- token transport ----------------------------------------------------------------------------------
+static double token_from_scheduler(gh_live* L, double overuse_ms, double next_burst_ms) {
+  L->token_requests.fetch_add(1, std::memory_order_relaxed);
+  int64_t t0 = gh_now_ns();
+  double q = 0.0;
+  if (gh_cfg.transport == 1) {
+    q = gemhook_pool_acquire(L->pool, L->slot, overuse_ms, next_burst_ms);
+  } else {
+    gemhook_request req;
+    gemhook_response rsp;
+    memset(&req, 0, sizeof(req));
+    req.type = GEMHOOK_REQ_QUOTA;
+    req.overuse_ms = overuse_ms;
+    req.burst_ms = next_burst_ms;
+    if (gh_rpc(&req, &rsp) != 0) {
+      fatal_or_disable(L, "failed to get a token from the scheduler");
+      return 1e12;
+    }
+    q = rsp.quota_ms;
+  }
+  L->token_wait_ms += (double)(gh_now_ns() - t0) / 1e6;
+  GH_DEBUG("token: overuse %.3f ms, next burst %.3f ms -> quota %.3f ms", overuse_ms, next_burst_ms, q);
+  return q;
+}
+
+// ---- overuse tracker ----------------------------------------------------------------------------------
+static void host_sync_locked(gh_live* L, int64_t now);
+static void resolve_pending_locked(gh_live* L, bool may_block);
+
+static void* tracker_main(void* arg) {
+  gh_live* L = (gh_live*)arg;
+  GH_CALL(cuCtxSetCurrent, L->ctx);
+  for (;;) {
+    pthread_mutex_lock(&L->trk_mu);
+    while (!L->trk_armed) pthread_cond_wait(&L->trk_start_cv, &L->trk_mu);
+    L->trk_armed = false;
+    // sleep until the token expires or a renewal wants the result earlier (hook.cpp:466-479)
+    struct timespec ts;
+    ts.tv_sec = L->trk_deadline_ns / 1000000000LL;
+    ts.tv_nsec = L->trk_deadline_ns % 1000000000LL;
+    while (!L->trk_intr) {
+      if (pthread_cond_timedwait(&L->trk_intr_cv, &L->trk_mu, &ts) == ETIMEDOUT) break;
+    }
+    L->trk_intr = false;
+    pthread_mutex_unlock(&L->trk_mu);
+
+    // drain everything issued so far: an event on the legacy default stream waits for all blocking
+    // streams (hook.cpp:449-453, 482-485); the events are reused, not leaked per token.
+    float elapsed_ms = 0.f;
+    if (!gh_cfg.dry_run) {
+      gh_host_sync_pre();  // close the running accounting segment on its own stream first
+      GH_CALL(cuEventRecord, L->ev_drain, (CUstream)0);
+      GH_CALL(cuEventSynchronize, L->ev_drain);
+      GH_CALL(cuEventElapsedTime, &elapsed_ms, L->ev_token, L->ev_drain);
+    }
+    pthread_mutex_lock(&L->mu);
+    int64_t now = gh_now_ns();
+    host_sync_locked(L, now);  // burst ends here; next launch re-evaluates the token
+    gemhook_gate_tracker_fire(L->gate, now, gh_cfg.dry_run ? (float)((double)(now - L->last_token_ns) / 1e6) : elapsed_ms);
+    if (L->cuda_ready && !gh_cfg.dry_run) resolve_pending_locked(L, false);
+    pthread_mutex_unlock(&L->mu);
+
+    pthread_mutex_lock(&L->trk_mu);
+    L->trk_done = true;
+    pthread_cond_broadcast(&L->trk_done_cv);
+    pthread_mutex_unlock(&L->trk_mu);
+  }
+  return nullptr;
+}
+
+static void wait_tracker(gh_live* L) {
+  pthread_mutex_lock(&L->trk_mu);
+  if (!L->trk_done) {
+    L->trk_intr = true;  // ask for the drain now (hook.cpp:527-533)
+    pthread_cond_signal(&L->trk_intr_cv);
+    while (!L->trk_done) pthread_cond_wait(&L->trk_done_cv, &L->trk_mu);
+  }
+  pthread_mutex_unlock(&L->trk_mu);
+}
+
+// ---- segments -----------------------------------------------------------------------------------------
+static void stage_record(gh_live* L, uint32_t launches, uint64_t ns) {
+  if (!L->stage[0]) return;
+  if (L->stage_n == L->stage_cap) return;  // flushed on the sync path; cannot overflow in practice
+  gemhook_record& r = L->stage[L->stage_cur][L->stage_n++];
+  r.slot = (uint32_t)L->slot;
+  r.launches = launches;
+  r.elapsed_ns = ns;
+  L->gpu_ns_host += ns;
+  L->segments.fetch_add(1, std::memory_order_relaxed);
+}
+
+static void flush_stage_locked(gh_live* L, bool force) {
+  if (!L->acct || L->stage_n == 0) return;
+  if (!force && L->stage_n < gh_cfg.flush_records) return;
+  // the other buffer's copy was issued at least one flush ago on the same stream: make sure it is done
+  gh_acct_push_async(L->acct, L->stage[L->stage_cur], L->stage_n);
+  L->stage_cur ^= 1;
+  L->stage_n = 0;
+  if (force) gemhook_acct_sync(L->acct);
+}
+
+static void resolve_pending_locked(gh_live* L, bool may_block);
+
+static void seg_begin_locked(gh_live* L, CUstream stream) {
+  if (gh_cfg.dry_run || !L->cuda_ready) return;
+  // events are a ring: never re-record one that an unresolved segment still refers to
+  if (L->npending > SEG_EVENTS / 2) resolve_pending_locked(L, true);
+  L->seg_head = (L->seg_head + 1) % SEG_EVENTS;
+  if (GH_CALL(cuEventRecord, L->seg_ev[L->seg_head], stream) != CUDA_SUCCESS) return;
+  L->seg_open = true;
+  L->seg_end_recorded = false;
+  L->seg_stream = stream;
+  L->seg_first_launch = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+}
+
+// every K launches inside a burst (GEMHOOK_SEG_LAUNCHES=K): close the running segment at this point
+void gh_segment_tick(CUstream stream) {
+  gh_live* L = g_live;
+  if (!L || !L->cuda_ready || gh_cfg.dry_run) return;
+  pthread_mutex_lock(&L->mu);
+  if (L->seg_open && L->npending < SEG_EVENTS / 2 - 1) {
+    int nxt = (L->seg_head + 1) % SEG_EVENTS;
+    if (GH_CALL(cuEventRecord, L->seg_ev[nxt], stream) == CUDA_SUCCESS) {
+      uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+      L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch)};
+      L->seg_head = nxt;
+      L->seg_first_launch = n;
+      L->seg_stream = stream;
+    }
+  }
+  pthread_mutex_unlock(&L->mu);
+}
+
+// before a synchronising driver call: mark the end of the running segment on its stream, so that the
+// event carries the completion time of the burst's last kernel rather than the host's return time
+void gh_host_sync_pre(void) {
+  gh_live* L = g_live;
+  if (!L || !L->cuda_ready || gh_cfg.dry_run || !L->seg_open) return;
+  pthread_mutex_lock(&L->mu);
+  if (L->seg_open && !L->seg_end_recorded && L->npending < SEG_EVENTS - 2) {
+    int nxt = (L->seg_head + 1) % SEG_EVENTS;
+    if (GH_CALL(cuEventRecord, L->seg_ev[nxt], L->seg_stream) == CUDA_SUCCESS) {
+      uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+      L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch)};
+      L->seg_head = nxt;
+      L->seg_end_recorded = true;
+    }
+  }
+  pthread_mutex_unlock(&L->mu);
+}
+
+// all pending events are complete after a host sync: turn them into records
+static void resolve_pending_locked(gh_live* L, bool may_block) {
+  int kept = 0;
+  for (int i = 0; i < L->npending; i++) {
+    gh_live::Pending& p = L->pending[i];
+    float ms = 0.f;
+    CUresult r = GH_CALL(cuEventElapsedTime, &ms, L->seg_ev[p.ev_begin], L->seg_ev[p.ev_end]);
+    if (r == CUDA_ERROR_NOT_READY && may_block) {
+      GH_CALL(cuEventSynchronize, L->seg_ev[p.ev_end]);
+      r = GH_CALL(cuEventElapsedTime, &ms, L->seg_ev[p.ev_begin], L->seg_ev[p.ev_end]);
+    }
+    if (r == CUDA_SUCCESS) {
+      double ns = (double)ms * 1e6;
+      stage_record(L, p.launches, ns > 0 ? (uint64_t)(ns + 0.5) : 0);
+    } else if (r == CUDA_ERROR_NOT_READY) {
+      L->pending[kept++] = p;  // a sync on another stream only: try again later
+    }
+  }
+  L->npending = kept;
+}
+
+static void host_sync_locked(gh_live* L, int64_t now) {
+  gemhook_gate_host_sync(L->gate, now);
+  gh_gate_open = 0;
+  L->seg_open = false;
+}
+
+void gh_host_sync_post(void) {
+  gh_live* L = gh_live_get();
+  if (!L || !L->enabled) return;
+  L->host_syncs.fetch_add(1, std::memory_order_relaxed);
+  pthread_mutex_lock(&L->mu);
+  host_sync_locked(L, gh_now_ns());
+  if (L->cuda_ready && !gh_cfg.dry_run) {
+    resolve_pending_locked(L, false);
+    flush_stage_locked(L, false);
+  }
+  pthread_mutex_unlock(&L->mu);
+}
+
+// ---- initialisation -----------------------------------------------------------------------------------
+void gh_register_exit_hook(void);
+static int read_quota_file_into_pool(gh_live* L) {
+  if (!gh_cfg.quota_file[0]) return 0;
+  FILE* f = fopen(gh_cfg.quota_file, "r");
+  if (!f) return -1;
+  char* text = (char*)calloc(1, 1 << 16);
+  size_t n = fread(text, 1, (1 << 16) - 1, f);
+  fclose(f);
+  text[n] = 0;
+  int rc = 0;
+  // only (re)load rows this pool does not know yet: a reload resets adaptive quotas (scheduler.cpp:203-212)
+  if (gemhook_pool_find(L->pool, gh_cfg.pod_name) < 0) rc = gemhook_pool_load_config(L->pool, text, gh_cfg.swap_columns);
+  free(text);
+  return rc;
+}
+
+static void live_init(void) {
+  gh_config_load();
+  gh_live* L = new gh_live();
+  L->gate = gemhook_gate_new();
+  if (gh_cfg.disabled || gh_driver_init() != 0) {
+    L->enabled = false;
+    g_live = L;
+    gh_gate_open = 1;  // pass-through
+    return;
+  }
+  L->enabled = true;
+  if (gh_cfg.seg_launches) {
+    uint32_t k = 1;
+    while (k < gh_cfg.seg_launches) k <<= 1;
+    gh_seg_mask = k - 1;
+  }
+  if (gh_cfg.transport == 1) {
+    L->pool = gemhook_pool_open(gh_cfg.pool_path, 1, gh_cfg.base_quota_ms, gh_cfg.min_quota_ms, gh_cfg.window_ms, 0);
+    if (!L->pool) {
+      fatal_or_disable(L, gemhook_last_error());
+    } else {
+      read_quota_file_into_pool(L);
+      L->slot = gemhook_pool_find(L->pool, gh_cfg.pod_name);
+      if (L->slot < 0) {
+        char msg[256];
+        snprintf(msg, sizeof(msg), "pod \"%s\" is not in the quota file / credit pool", gh_cfg.pod_name);
+        fatal_or_disable(L, msg);
+        L->slot = 0;
+      }
+    }
+  } else if (!gh_cfg.scheduler_ip[0]) {
+    // reference: exit(-1) when /kubeshare/library/schedulerIP.txt is missing (hook.cpp:234-237)
+    fatal_or_disable(L, "scheduler IP file missing (set GEMHOOK_SCHEDULER_IP or /kubeshare/library/schedulerIP.txt)");
+  }
+  g_live = L;
+  if (!L->enabled) gh_gate_open = 1;
+  // registered after the driver's own atexit handlers (cuInit ran before the first intercepted call),
+  // so it runs BEFORE them and CUDA is still usable for the final flush
+  gh_register_exit_hook();
+  GH_INFO("gemhook ready: pod \"%s\", transport %s, segment mask %#x", gh_cfg.pod_name,
+          gh_cfg.transport ? "pool" : "tcp", gh_seg_mask);
+}
+
+gh_live* gh_live_get(void) {
+  pthread_once(&live_once, live_init);
+  return g_live;
+}
+
+// CUDA-side objects need a current context: created at the first launch (hook.cpp:754-764 does the same
+// from initialize()).  Caller holds L->mu.
+static void cuda_init_locked(gh_live* L) {
+  if (L->cuda_ready) return;
+  L->cuda_ready = true;
+  pthread_condattr_t attr;
+  pthread_condattr_init(&attr);
+  pthread_condattr_setclock(&attr, CLOCK_MONOTONIC);
+  pthread_cond_init(&L->trk_intr_cv, &attr);
+  GH_CALL(cuCtxGetCurrent, &L->ctx);
+  if (!gh_cfg.dry_run) {
+    GH_CALL(cuEventCreate, &L->ev_token, CU_EVENT_DEFAULT);
+    GH_CALL(cuEventCreate, &L->ev_drain, CU_EVENT_DEFAULT);
+    for (int i = 0; i < SEG_EVENTS; i++) GH_CALL(cuEventCreate, &L->seg_ev[i], CU_EVENT_DEFAULT);
+    uint32_t nslots = L->pool ? (uint32_t)gemhook_pool_nslots(L->pool) : 1;
+    if (nslots < 1) nslots = 1;
+    L->acct = gemhook_acct_create(nslots, 1u << 14);
+    if (!L->acct) {
+      // no silent CPU accounting: say so, keep gating alive
+      fprintf(stderr, "[gemhook %d] device accounting unavailable: %s\n", (int)getpid(), gemhook_last_error());
+    } else {
+      L->stage_cap = gh_cfg.flush_records * 4 > 1024 ? gh_cfg.flush_records * 4 : 1024;
+      for (int b = 0; b < 2; b++) {
+        void* hp = nullptr;
+        if (GH_CALL(cuMemHostAlloc, &hp, L->stage_cap * sizeof(gemhook_record), CU_MEMHOSTALLOC_PORTABLE) == CUDA_SUCCESS)
+          L->stage[b] = (gemhook_record*)hp;
+      }
+      if (L->pool) {
+        // "shared-pinned": the credit pool is page-locked and device-mapped, so device code (and peers'
+        // device code) can read the same words the host arbitrates on
+        size_t bytes = 0;
+        void* base = gh_pool_region(L->pool, &bytes);
+        CUresult r = GH_CALL(cuMemHostRegister_v2, base, bytes, CU_MEMHOSTREGISTER_PORTABLE | CU_MEMHOSTREGISTER_DEVICEMAP);
+        GH_DEBUG("cuMemHostRegister(pool, %zu B) -> %d", bytes, (int)r);
+      }
+    }
+  }
+  pthread_create(&L->trk_tid, nullptr, tracker_main, L);
+  pthread_detach(L->trk_tid);
+  // first token request; its quota is discarded so that the first launch renews immediately (hook.cpp:766-768)
+  pthread_mutex_unlock(&L->mu);
+  token_from_scheduler(L, 0.0, 0.0);
+  pthread_mutex_lock(&L->mu);
+}
+
+// ---- launch slow path ---------------------------------------------------------------------------------
+void gh_launch_slow(CUstream stream) {
+  gh_live* L = gh_live_get();
+  if (!L || !L->enabled) return;
+  L->slow_path.fetch_add(1, std::memory_order_relaxed);
+  pthread_mutex_lock(&L->mu);
+  cuda_init_locked(L);
+  while (L->renewing) pthread_cond_wait(&L->renew_cv, &L->mu);
+  int64_t now = gh_now_ns();
+  if (L->enabled && gemhook_gate_launch_begin(L->gate, now)) {
+    L->renewing = true;
+    pthread_mutex_unlock(&L->mu);
+    wait_tracker(L);  // GPU drained, overuse known
+    pthread_mutex_lock(&L->mu);
+    double overuse = 0, next_burst = 0;
+    int64_t t_req = gh_now_ns();
+    gemhook_gate_renew_request(L->gate, t_req, &overuse, &next_burst);
+    if (L->last_token_ns) {
+      // what the scheduler's ledger will hold for the token we are returning:
+      // end = min(now, start + quota + overuse) (reference scheduler.cpp:123-153)
+      double held = (double)(t_req - L->last_token_ns) / 1e6, cap = L->last_quota_ms + overuse;
+      L->accumulated_token_ms += held < cap ? held : cap;
+    }
+    pthread_mutex_unlock(&L->mu);
+    double quota = token_from_scheduler(L, overuse, next_burst);
+    pthread_mutex_lock(&L->mu);
+    if (!gh_cfg.dry_run) GH_CALL(cuEventRecord, L->ev_token, (CUstream)0);  // hook.cpp:543
+    now = gh_now_ns();
+    gemhook_gate_renew_granted(L->gate, now, quota);
+    L->last_token_ns = now;
+    L->last_quota_ms = quota;
+    pthread_mutex_lock(&L->trk_mu);
+    L->trk_done = false;
+    L->trk_armed = true;
+    L->trk_intr = false;
+    double q = quota > 0 ? quota : 0;
+    if (q > 8.64e7) q = 8.64e7;  // clamp absurd quotas to a day to keep the timespec sane
+    L->trk_deadline_ns = now + (int64_t)(q * 1e6);
+    pthread_cond_signal(&L->trk_start_cv);
+    pthread_mutex_unlock(&L->trk_mu);
+    L->renewing = false;
+    pthread_cond_broadcast(&L->renew_cv);
+  }
+  gemhook_gate_launch_end(L->gate, gh_now_ns());
+  seg_begin_locked(L, stream);
+  gh_gate_open = 1;
+  pthread_mutex_unlock(&L->mu);
+}
+
+// ---- introspection ------------------------------------------------------------------------------------
+GH_EXPORT int gemhook_flush(void) {
+  gh_live* L = g_live;
+  if (!L || !L->cuda_ready || gh_cfg.dry_run) return 0;
+  pthread_mutex_lock(&L->mu);
+  if (L->seg_open && !L->seg_end_recorded) {
+    pthread_mutex_unlock(&L->mu);
+    gh_host_sync_pre();
+    pthread_mutex_lock(&L->mu);
+  }
+  resolve_pending_locked(L, true);
+  flush_stage_locked(L, true);
+  if (L->acct && L->pool) {
+    uint64_t tot[GEMHOOK_MAX_SLOTS * 3];
+    if (gemhook_acct_read_totals(L->acct, tot, nullptr) == 0)
+      gh_pool_publish_usage(L->pool, L->slot, tot[L->slot * 3], tot[L->slot * 3 + 1]);
+  }
+  pthread_mutex_unlock(&L->mu);
+  return 0;
+}
+
+GH_EXPORT int gemhook_get_stats(gemhook_stats* out) {
+  if (!out) return -1;
+  memset(out, 0, sizeof(*out));
+  gh_live* L = g_live;
+  if (!L) return -1;
+  uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+  out->launches = n;
+  out->slow_path = L->slow_path.load();
+  out->fast_path = n - (out->slow_path < n ? out->slow_path : n);
+  out->token_requests = L->token_requests.load();
+  out->host_syncs = L->host_syncs.load();
+  out->segments = L->segments.load();
+  out->acct_kernels = L->acct ? gemhook_acct_kernel_launches(L->acct) : 0;
+  if (L->acct) {
+    uint64_t tot[GEMHOOK_MAX_SLOTS * 3];
+    if (gemhook_acct_read_totals(L->acct, tot, nullptr) == 0) out->gpu_ns = tot[L->slot * 3];
+  }
+  gh_mem_info(&out->mem_used, &out->mem_limit);
+  out->mem_used = out->mem_limit - out->mem_used;  // gh_mem_info returns (free, total)
+  out->quota_ms = gemhook_gate_quota_ms(L->gate);
+  out->overuse_ms = gemhook_gate_overuse_ms(L->gate);
+  out->token_wait_ms = L->token_wait_ms;
+  out->accumulated_token_ms = L->accumulated_token_ms;
+  return 0;
+}
+
+// GEMHOOK_STATS_FILE=<path with optional %d for the pid>: one JSON object written at process exit, used
+// by bench.py and the tests to collect per-client numbers without touching the application.
+uint64_t gh_mem_denied(void);
+void gh_register_exit_hook(void);
+static void write_stats_file(void) {
+  const char* pat = getenv("GEMHOOK_STATS_FILE");
+  gh_live* L = g_live;
+  if (!pat || !*pat || !L) return;
+  gemhook_flush();
+  gemhook_stats s;
+  gemhook_get_stats(&s);
+  char path[600];
+  snprintf(path, sizeof(path), pat, (int)getpid());
+  FILE* f = fopen(path, "w");
+  if (!f) return;
+  fprintf(f,
+          "{\"pod\": \"%s\", \"pid\": %d, \"launches\": %llu, \"fast_path\": %llu, \"slow_path\": %llu, "
+          "\"token_requests\": %llu, \"host_syncs\": %llu, \"segments\": %llu, \"acct_kernels\": %llu, "
+          "\"gpu_ns\": %llu, \"gpu_ns_host\": %llu, \"mem_used\": %llu, \"mem_limit\": %llu, \"allocs_denied\": %llu, "
+          "\"quota_ms\": %.6f, \"overuse_ms\": %.6f, \"token_wait_ms\": %.6f, \"accumulated_token_ms\": %.6f}\n",
+          gh_cfg.pod_name, (int)getpid(), (unsigned long long)s.launches, (unsigned long long)s.fast_path,
+          (unsigned long long)s.slow_path, (unsigned long long)s.token_requests, (unsigned long long)s.host_syncs,
+          (unsigned long long)s.segments, (unsigned long long)s.acct_kernels, (unsigned long long)s.gpu_ns,
+          (unsigned long long)L->gpu_ns_host, (unsigned long long)s.mem_used, (unsigned long long)s.mem_limit,
+          (unsigned long long)gh_mem_denied(), s.quota_ms, s.overuse_ms, s.token_wait_ms, s.accumulated_token_ms);
+  fclose(f);
+}
+
+void gh_register_exit_hook(void) { atexit(write_stats_file); }
+
+// accessors for gh_mem.cpp / gh_interpose.cpp
+extern "C" gemhook_pool* gh_live_pool(void) { return g_live ? g_live->pool : nullptr; }
+extern "C" int gh_live_slot(void) { return g_live ? g_live->slot : 0; }
+extern "C" int gh_live_enabled(void) { return (g_live && g_live->enabled) ? 1 : 0; }

@@ -1,0 +1,110 @@
+// gh_internal.h -- declarations shared by the libgemhook.so.1 translation units (not installed).
+#ifndef GH_INTERNAL_H
+#define GH_INTERNAL_H
+
+#include <cuda.h>
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <time.h>
+
+#include "../../include/gemhook.h"
+
+#define GH_EXPORT extern "C" __attribute__((visibility("default")))
+
+// ---- logging / errors -----------------------------------------------------------------------------
+// GEMHOOK_LOG=0 silent (default) | 1 errors+info | 2 debug.  Never opens a file per call (the reference's
+// hINFO/hERROR open+append+close /kubeshare/log/hook.log every time, reference debug.cpp:48-60).
+extern int gh_log_level;
+void gh_log(int level, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+void gh_set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+#define GH_INFO(...) do { if (gh_log_level >= 1) gh_log(1, __VA_ARGS__); } while (0)
+#define GH_DEBUG(...) do { if (gh_log_level >= 2) gh_log(2, __VA_ARGS__); } while (0)
+
+static inline int64_t gh_now_ns(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (int64_t)ts.tv_sec * 1000000000LL + ts.tv_nsec;
+}
+
+// ---- the real driver ------------------------------------------------------------------------------
+// Every driver entry point the library itself calls, resolved from the real libcuda.so.1 with the libc
+// dlsym (never through our own interposers).
+#define GH_REAL_DRIVER_FUNCS(X)                                                                        \
+  X(cuInit) X(cuDriverGetVersion) X(cuGetErrorString)                                                  \
+  X(cuCtxGetCurrent) X(cuCtxSetCurrent) X(cuCtxGetDevice) X(cuCtxSynchronize)                         \
+  X(cuDeviceGetAttribute) X(cuDeviceTotalMem_v2) X(cuMemGetInfo_v2)                                    \
+  X(cuModuleLoadData) X(cuModuleGetFunction) X(cuModuleUnload) X(cuFuncSetAttribute)                  \
+  X(cuOccupancyMaxActiveBlocksPerMultiprocessor)                                                       \
+  X(cuStreamCreate) X(cuStreamDestroy_v2) X(cuStreamSynchronize)                                       \
+  X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime)   \
+  X(cuEventQuery)                                                                                      \
+  X(cuMemAlloc_v2) X(cuMemFree_v2) X(cuMemAllocManaged) X(cuMemAllocPitch_v2)                          \
+  X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemsetD8Async)                                   \
+  X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostGetDevicePointer_v2)                                   \
+  X(cuMemHostRegister_v2) X(cuMemHostUnregister)                                                       \
+  X(cuLaunchKernel) X(cuLaunchCooperativeKernel)                                                       \
+  X(cuArrayCreate_v2) X(cuArray3DCreate_v2) X(cuArrayDestroy)                                          \
+  X(cuMipmappedArrayCreate) X(cuMipmappedArrayDestroy)                                                 \
+  X(cuMemcpyAtoH_v2) X(cuMemcpyDtoH_v2) X(cuMemcpyHtoA_v2) X(cuMemcpyHtoD_v2)
+
+struct gh_driver {
+#define X(name) void* name;
+  GH_REAL_DRIVER_FUNCS(X)
+#undef X
+  void* gpa_legacy;           // cuGetProcAddress, legacy 4-arg
+  void* gpa_v2;               // cuGetProcAddress_v2, 5-arg
+  void* handle;               // dlopen handle of the real libcuda
+};
+extern gh_driver gh_real;
+// Resolve the table (idempotent, thread-safe). Returns 0, or -1 when libcuda cannot be opened.
+int gh_driver_init(void);
+void* gh_true_dlsym(void* handle, const char* symbol);
+#define GH_CALL(name, ...) (((decltype(&name))gh_real.name)(__VA_ARGS__))
+
+// ---- predictor / gate (gh_gate.cpp) ---------------------------------------------------------------
+struct gh_predictor;
+struct gemhook_predictor;
+struct gemhook_gate;
+
+// ---- live hook state (gh_hook.cpp) ----------------------------------------------------------------
+struct gh_live;
+gh_live* gh_live_get(void);  // lazily initialised process singleton (NULL if disabled)
+
+// launch path (called from the interposers in gh_driver.cpp)
+void gh_launch_slow(CUstream stream);
+void gh_host_sync_pre(void);
+void gh_host_sync_post(void);
+extern volatile uint32_t gh_gate_open;     // 1: burst ongoing and token valid -> fast path
+extern uint64_t gh_launch_count;           // intercepted launches (relaxed)
+extern uint32_t gh_seg_mask;               // segment every (mask+1) launches; 0xffffffff = burst edges only
+void gh_segment_tick(CUstream stream);
+
+// gpu_mem cap (gh_mem.cpp)
+int gh_mem_reserve(uint64_t bytes);        // 1 ok, 0 denied
+void gh_mem_commit(uint64_t key, uint64_t bytes);
+void gh_mem_unreserve(uint64_t bytes);
+void gh_mem_free_key(uint64_t key);
+void gh_mem_info(uint64_t* free_b, uint64_t* total_b);
+
+// config (gh_config.cpp)
+struct gh_config {
+  char pod_name[72];
+  char pool_path[512];
+  char quota_file[512];
+  char scheduler_ip[64];
+  int pod_manager_port;
+  int transport;          // 0 = tcp (reference daemons), 1 = shared credit pool
+  int swap_columns;
+  int dry_run;            // no accounting kernels / events (stub driver)
+  int extra_hooks;
+  int exit_on_failure;    // reference behaviour: exit() when the scheduler is unreachable
+  uint32_t seg_launches;  // K
+  uint32_t flush_records;
+  double base_quota_ms, min_quota_ms, window_ms;
+  int disabled;
+};
+extern gh_config gh_cfg;
+void gh_config_load(void);
+
+#endif

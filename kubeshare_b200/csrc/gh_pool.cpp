@@ -1,0 +1,544 @@
+// gh_pool.cpp -- the shared credit pool: one file-backed MAP_SHARED region per GPU that replaces the
+// hook -> gem-pmgr -> gem-schd TCP round trips (reference hook.cpp:300-328, 425-446) for co-resident
+// clients, and the token policy that runs inside it.
+//
+// What stays the reference's (bit-exact, see tests/test_pool_policy.py against the oracle):
+//   * per-client adaptive quota        scheduler.cpp:160-174  (EMA 0.5, clamp [min_quota, max_frac*window])
+//   * ledger of granted tokens          scheduler.cpp:144-153  Record(); :123-142 update_return_time()
+//   * windowed usage with overlap split scheduler.cpp:281-367
+//   * eligibility + ordering            scheduler.cpp:369-398, schd-priority.cpp:19-26
+//   * ONE outstanding token per GPU     scheduler.cpp:461-529
+//   * gpu_mem counter, requested bytes  pod-manager.cpp:295-313, hook.cpp:590-601
+// What is new: there is no daemon in the decision path.  Whoever needs a decision takes a short
+// spin lock in the shared region (held for microseconds), runs the policy over the shared ledger and
+// publishes the grant into the winner's slot; a renewal on an uncontended GPU is a few hundred
+// nanoseconds of shared-memory traffic and no context switch.  Clients that must wait (throttled, or
+// another client holds the token) futex-wait on their own slot word.
+//
+// The region is plain memory: it can be cuMemHostRegister'ed (gh_hook.cpp does) so the device sees
+// the same counters ("shared-pinned").
+#include <errno.h>
+#include <fcntl.h>
+#include <linux/futex.h>
+#include <sched.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+#include "gh_internal.h"
+
+namespace {
+
+const uint64_t POOL_MAGIC = 0x314c4f4f504d4547ULL;  // "GEMPOOL1"
+const uint32_t POOL_VERSION = 1;
+const uint32_t LEDGER_CAP = 8192;
+enum { ST_IDLE = 0, ST_WAITING = 1, ST_GRANTED = 2 };
+
+struct alignas(64) Slot {
+  // line 0: identity
+  char name[64];
+  // line 1: configuration + adaptive quota state (ClientInfo)
+  double min_frac, max_frac;
+  uint64_t mem_limit;
+  double quota;   // quota_
+  double burst;   // burst_
+  uint32_t configured;
+  uint32_t _pad0;
+  double last_start, last_end;  // latest token of this client in the FULL history (never pruned)
+  // line 2: request / grant mailbox
+  std::atomic<uint32_t> state;
+  uint32_t _pad1;
+  double arrived_ms;
+  double granted_quota;
+  uint64_t req_seq;  // order of arrival (the candidates list is FIFO)
+  uint64_t grants;
+  double closed_ms;  // sum(end - start) over this client's finished tokens (full history)
+  uint64_t _pad2[2];
+  // line 3: counters other parties read
+  std::atomic<uint64_t> mem_used;
+  std::atomic<uint64_t> gpu_ns, launches;
+  uint64_t _pad3[5];
+};
+static_assert(sizeof(Slot) == 256, "slot layout");
+
+struct Span {
+  int32_t slot;
+  int32_t _pad;
+  double start, end;
+};
+
+struct alignas(64) Header {
+  uint64_t magic;
+  uint32_t version, nslots_max;
+  double base_quota, min_quota, window;
+  int64_t start_ns;
+  std::atomic<uint32_t> ready;
+  std::atomic<uint32_t> nslots;
+  // arbitration lock (owner pid, for dead-owner recovery)
+  alignas(64) std::atomic<uint32_t> lock;
+  uint32_t _padl;
+  std::atomic<int64_t> lock_ns;
+  // token state
+  alignas(64) int32_t holder;  // slot holding the outstanding token or -1
+  int32_t _padh;
+  double deadline_ms;
+  uint64_t next_req_seq;
+  uint64_t total_grants;
+  uint32_t ledger_len;
+  uint32_t ledger_dropped;
+};
+
+struct Region {
+  Header h;
+  Slot slots[GEMHOOK_MAX_SLOTS];
+  Span ledger[LEDGER_CAP];
+};
+
+long futex(std::atomic<uint32_t>* addr, int op, uint32_t val, const struct timespec* ts) {
+  return syscall(SYS_futex, (uint32_t*)addr, op, val, ts, nullptr, 0);
+}
+
+struct Stamp {
+  int32_t slot;
+  double t;  // negative = start
+};
+struct Ranked {
+  double missing, remaining, usage, arrived;
+  int slot;
+};
+// schd-priority.cpp:19-26
+bool rank_before(const Ranked& a, const Ranked& b) {
+  if (a.missing > 0 && b.missing > 0) return a.missing / (a.missing + a.usage) > b.missing / (b.missing + b.usage);
+  if (a.missing > 0 && b.missing < 0) return true;
+  if (a.missing < 0 && b.missing > 0) return false;
+  return a.usage < b.usage;
+}
+
+}  // namespace
+
+struct gemhook_pool {
+  Region* r = nullptr;
+  int fd = -1;
+  bool anonymous = false;
+
+  void lock() {
+    uint32_t me = (uint32_t)getpid();
+    int spins = 0;
+    for (;;) {
+      uint32_t exp = 0;
+      if (r->h.lock.compare_exchange_weak(exp, me, std::memory_order_acquire)) break;
+      if (++spins > 2000) {
+        // owner may have died inside the critical section: steal after 100 ms
+        int64_t t = r->h.lock_ns.load(std::memory_order_relaxed);
+        if (t && gh_now_ns() - t > 100000000LL) {
+          if (r->h.lock.compare_exchange_strong(exp, me, std::memory_order_acquire)) break;
+        }
+        sched_yield();
+        spins = 0;
+      }
+      __builtin_ia32_pause();
+    }
+    r->h.lock_ns.store(gh_now_ns(), std::memory_order_relaxed);
+  }
+  void unlock() {
+    r->h.lock_ns.store(0, std::memory_order_relaxed);
+    r->h.lock.store(0, std::memory_order_release);
+  }
+
+  // scheduler.cpp:281-367 -- prune the ledger and compute per-slot usage inside the window
+  void window_usage(double now, double* usage, double& wsize, double& wstart) {
+    Header& h = r->h;
+    wsize = h.window;
+    wstart = now - h.window;
+    if (wstart < 0) wsize = now;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < h.ledger_len; i++)
+      if (!(r->ledger[i].end < wstart)) r->ledger[k++] = r->ledger[i];
+    h.ledger_len = k;
+
+    std::vector<Stamp> st;
+    st.reserve(2 * k);
+    for (uint32_t i = 0; i < k; i++) {
+      st.push_back({r->ledger[i].slot, -r->ledger[i].start});
+      st.push_back({r->ledger[i].slot, r->ledger[i].end});
+      usage[r->ledger[i].slot] = 0;
+    }
+    std::sort(st.begin(), st.end(), [](Stamp a, Stamp b) { return std::abs(a.t) < std::abs(b.t); });
+    std::vector<int32_t> live;
+    int live_cnt = 0;
+    size_t j = 0;
+    for (; j < st.size(); j++) {
+      if (std::abs(st[j].t) <= wstart) {
+        live_cnt++;
+        live.push_back(st[j].slot);
+      } else {
+        break;
+      }
+    }
+    double cur = wstart;
+    for (size_t i = j; i < st.size(); i++) {
+      for (size_t q = 0; q < live.size(); q++) usage[live[q]] += (std::abs(st[i].t) - cur) / live_cnt;
+      if (st[i].t < 0) {
+        live.push_back(st[i].slot);
+        live_cnt++;
+      } else {
+        for (size_t q = 0; q < live.size(); q++)
+          if (live[q] == st[i].slot) {
+            live.erase(live.begin() + q);
+            break;
+          }
+        live_cnt--;
+      }
+      cur = std::abs(st[i].t);
+    }
+  }
+
+  // caller holds the lock
+  int schedule_locked(double now, int* slot_out, double* quota_out, double* sleep_out) {
+    Header& h = r->h;
+    uint32_t n = h.nslots.load(std::memory_order_relaxed);
+    if (h.holder >= 0) {
+      // scheduler.cpp:501-521: wait until the holder asks again or its quota times out
+      bool back = r->slots[h.holder].state.load(std::memory_order_relaxed) == ST_WAITING;
+      if (!back && now < h.deadline_ms) {
+        if (sleep_out) *sleep_out = h.deadline_ms - now;
+        return -2;
+      }
+      h.holder = -1;
+    }
+    // candidates in arrival order
+    int order[GEMHOOK_MAX_SLOTS];
+    int nc = 0;
+    for (uint32_t i = 0; i < n; i++)
+      if (r->slots[i].state.load(std::memory_order_relaxed) == ST_WAITING) order[nc++] = (int)i;
+    if (nc == 0) return -1;
+    std::sort(order, order + nc, [&](int a, int b) { return r->slots[a].req_seq < r->slots[b].req_seq; });
+
+    double usage[GEMHOOK_MAX_SLOTS];
+    for (uint32_t i = 0; i < n; i++) usage[i] = 0;
+    double wsize, wstart;
+    window_usage(now, usage, wsize, wstart);
+
+    int pick = -1;
+    bool head_seen = false;  // scheduler.cpp:312-320: head of the queue with no recent history goes first
+    for (uint32_t i = 0; i < h.ledger_len; i++)
+      if (r->ledger[i].slot == order[0]) {
+        head_seen = true;
+        break;
+      }
+    if (!head_seen) {
+      pick = order[0];
+    } else {
+      std::vector<Ranked> ok;
+      for (int c = 0; c < nc; c++) {
+        Slot& s = r->slots[order[c]];
+        double limit = s.max_frac * wsize, require = s.min_frac * wsize;
+        double missing = require - usage[order[c]], remaining = limit - usage[order[c]];
+        if (remaining > 0) ok.push_back({missing, remaining, usage[order[c]], s.arrived_ms, order[c]});
+      }
+      if (ok.empty()) {  // scheduler.cpp:383-390
+        if (sleep_out) *sleep_out = r->ledger[0].end - wstart;
+        return 0;
+      }
+      std::sort(ok.begin(), ok.end(), rank_before);
+      pick = ok[0].slot;
+    }
+
+    // get_quota (scheduler.cpp:160-174) + Record (scheduler.cpp:144-153)
+    Slot& s = r->slots[pick];
+    if (s.burst < 1e-9) {
+      s.quota = h.base_quota;
+    } else {
+      s.quota = s.burst * 0.5 + s.quota * (1 - 0.5);
+      s.quota = std::max(s.quota, h.min_quota);
+      s.quota = std::min(s.quota, s.max_frac * h.window);
+    }
+    if (h.ledger_len == LEDGER_CAP) {  // cannot happen with sane quotas; keep the newest entries
+      memmove(&r->ledger[0], &r->ledger[1], sizeof(Span) * (LEDGER_CAP - 1));
+      h.ledger_len--;
+      h.ledger_dropped++;
+    }
+    r->ledger[h.ledger_len++] = Span{pick, 0, now, now + s.quota};
+    if (s.grants) s.closed_ms += s.last_end - s.last_start;
+    s.last_start = now;
+    s.last_end = now + s.quota;
+    s.grants++;
+    h.total_grants++;
+    h.holder = pick;
+    h.deadline_ms = now + s.quota;
+    s.granted_quota = s.quota;
+    s.state.store(ST_GRANTED, std::memory_order_release);
+    if (slot_out) *slot_out = pick;
+    if (quota_out) *quota_out = s.quota;
+    return 1;
+  }
+
+  double now_ms() const { return (double)((gh_now_ns() - r->h.start_ns) / 1000) / 1e3; }  // scheduler.cpp:107-109
+};
+
+GH_EXPORT gemhook_pool* gemhook_pool_open(const char* path, int create, double base_quota_ms, double min_quota_ms,
+                                          double window_ms, int64_t start_ns) {
+  gemhook_pool* p = new gemhook_pool();
+  size_t bytes = sizeof(Region);
+  void* m = MAP_FAILED;
+  bool fresh = false;
+  if (!path || !*path) {  // private pool (tests, single-process use)
+    m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    p->anonymous = true;
+    fresh = true;
+  } else {
+    int fd = open(path, create ? (O_RDWR | O_CREAT) : O_RDWR, 0666);
+    if (fd < 0) {
+      gh_set_error("cannot open pool file %s: %s", path, strerror(errno));
+      delete p;
+      return nullptr;
+    }
+    struct stat st;
+    fstat(fd, &st);
+    if ((size_t)st.st_size < bytes) {
+      if (!create || ftruncate(fd, (off_t)bytes) != 0) {
+        gh_set_error("pool file %s is too small (%lld bytes) and may not be created", path, (long long)st.st_size);
+        close(fd);
+        delete p;
+        return nullptr;
+      }
+    }
+    m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    p->fd = fd;
+  }
+  if (m == MAP_FAILED) {
+    gh_set_error("mmap of the credit pool failed: %s", strerror(errno));
+    if (p->fd >= 0) close(p->fd);
+    delete p;
+    return nullptr;
+  }
+  p->r = (Region*)m;
+  Header& h = p->r->h;
+  // first opener initialises: claim with CAS on magic (file content starts as zeros)
+  uint64_t zero = 0;
+  std::atomic<uint64_t>* magic = reinterpret_cast<std::atomic<uint64_t>*>(&h.magic);
+  if (fresh || (create && magic->compare_exchange_strong(zero, POOL_MAGIC))) {
+    h.magic = POOL_MAGIC;
+    h.version = POOL_VERSION;
+    h.nslots_max = GEMHOOK_MAX_SLOTS;
+    h.base_quota = base_quota_ms;
+    h.min_quota = min_quota_ms;
+    h.window = window_ms;
+    h.start_ns = start_ns ? start_ns : gh_now_ns();
+    h.holder = -1;
+    h.nslots.store(0);
+    h.ready.store(1, std::memory_order_release);
+  } else {
+    for (int i = 0; i < 20000 && !h.ready.load(std::memory_order_acquire); i++) usleep(100);
+    if (h.magic != POOL_MAGIC || !h.ready.load() || h.version != POOL_VERSION) {
+      gh_set_error("%s is not an initialised gemhook credit pool", path);
+      gemhook_pool_close(p);
+      return nullptr;
+    }
+  }
+  return p;
+}
+
+GH_EXPORT void gemhook_pool_close(gemhook_pool* p) {
+  if (!p) return;
+  if (p->r) munmap(p->r, sizeof(Region));
+  if (p->fd >= 0) close(p->fd);
+  delete p;
+}
+
+void* gh_pool_region(gemhook_pool* p, size_t* bytes) {
+  if (bytes) *bytes = sizeof(Region);
+  return p ? (void*)p->r : nullptr;
+}
+
+// read_resource_config (scheduler.cpp:183-217): "N" then N rows "name c2 c3 mem"; a re-read replaces the
+// client's ClientInfo, i.e. its adaptive quota restarts from the base quota; usage history is kept.
+GH_EXPORT int gemhook_pool_load_config(gemhook_pool* p, const char* text, int swap_columns) {
+  if (!p || !text) return -1;
+  const char* c = text;
+  char* end = nullptr;
+  long n = strtol(c, &end, 10);
+  if (end == c || n < 0) {
+    gh_set_error("quota file: bad client count");
+    return -1;
+  }
+  c = end;
+  p->lock();
+  Header& h = p->r->h;
+  int loaded = 0;
+  for (long i = 0; i < n; i++) {
+    char name[64];
+    double c2, c3;
+    unsigned long long mem;
+    int used = 0;
+    if (sscanf(c, " %63s %lf %lf %llu%n", name, &c2, &c3, &mem, &used) != 4) break;
+    c += used;
+    uint32_t ns = h.nslots.load(std::memory_order_relaxed);
+    int idx = -1;
+    for (uint32_t s = 0; s < ns; s++)
+      if (!strncmp(p->r->slots[s].name, name, sizeof(p->r->slots[s].name))) idx = (int)s;
+    if (idx < 0) {
+      if (ns >= GEMHOOK_MAX_SLOTS) {
+        gh_set_error("quota file lists more than %d clients", GEMHOOK_MAX_SLOTS);
+        break;
+      }
+      idx = (int)ns;
+      memset((void*)&p->r->slots[idx], 0, sizeof(Slot));
+      snprintf(p->r->slots[idx].name, sizeof(p->r->slots[idx].name), "%s", name);
+      h.nslots.store(ns + 1, std::memory_order_release);
+    }
+    Slot& s = p->r->slots[idx];
+    s.min_frac = swap_columns ? c3 : c2;
+    s.max_frac = swap_columns ? c2 : c3;
+    s.mem_limit = mem;
+    s.quota = h.base_quota;
+    s.burst = 0.0;
+    s.configured = 1;
+    loaded++;
+  }
+  p->unlock();
+  return loaded == n ? (int)n : -1;
+}
+
+GH_EXPORT int gemhook_pool_find(const gemhook_pool* p, const char* name) {
+  uint32_t ns = p->r->h.nslots.load(std::memory_order_acquire);
+  for (uint32_t s = 0; s < ns; s++)
+    if (!strncmp(p->r->slots[s].name, name, sizeof(p->r->slots[s].name))) return (int)s;
+  return -1;
+}
+GH_EXPORT int gemhook_pool_nslots(const gemhook_pool* p) { return (int)p->r->h.nslots.load(std::memory_order_acquire); }
+
+// handle_message(REQ_QUOTA) (scheduler.cpp:417-429): update_return_time + set_burst + enqueue
+static void request_locked(gemhook_pool* p, int slot, double now, double overuse, double burst) {
+  Header& h = p->r->h;
+  Slot& s = p->r->slots[slot];
+  for (uint32_t i = h.ledger_len; i-- > 0;) {
+    if (p->r->ledger[i].slot == slot) {
+      p->r->ledger[i].end = std::min(now, p->r->ledger[i].end + overuse);
+      break;
+    }
+  }
+  if (s.grants) s.last_end = std::min(now, s.last_end + overuse);
+  s.burst = burst;
+  s.arrived_ms = now;
+  s.req_seq = ++h.next_req_seq;
+  s.state.store(ST_WAITING, std::memory_order_release);
+}
+
+GH_EXPORT int gemhook_pool_request(gemhook_pool* p, int slot, double now_ms, double overuse_ms, double burst_ms) {
+  if (!p || slot < 0 || slot >= gemhook_pool_nslots(p)) return -1;
+  p->lock();
+  request_locked(p, slot, now_ms, overuse_ms, burst_ms);
+  p->unlock();
+  return 0;
+}
+
+GH_EXPORT int gemhook_pool_schedule(gemhook_pool* p, double now_ms, int* slot_out, double* quota_out, double* sleep_ms_out) {
+  p->lock();
+  int rc = p->schedule_locked(now_ms, slot_out, quota_out, sleep_ms_out);
+  p->unlock();
+  return rc;
+}
+
+GH_EXPORT double gemhook_pool_usage(gemhook_pool* p, int slot, double now_ms) {
+  double usage[GEMHOOK_MAX_SLOTS] = {0};
+  double a, b;
+  p->lock();
+  p->window_usage(now_ms, usage, a, b);
+  p->unlock();
+  return usage[slot];
+}
+
+GH_EXPORT size_t gemhook_pool_history(const gemhook_pool* p, int* slots, double* starts, double* ends, size_t cap) {
+  size_t n = p->r->h.ledger_len;
+  for (size_t i = 0; i < n && i < cap; i++) {
+    if (slots) slots[i] = p->r->ledger[i].slot;
+    if (starts) starts[i] = p->r->ledger[i].start;
+    if (ends) ends[i] = p->r->ledger[i].end;
+  }
+  return n;
+}
+
+GH_EXPORT double gemhook_pool_accumulated_ms(const gemhook_pool* p, int slot) {
+  const Slot& s = p->r->slots[slot];
+  return s.grants ? s.closed_ms + (s.last_end - s.last_start) : 0.0;
+}
+
+// Live acquisition: post the request, then arbitrate/wait until OUR slot is granted.
+GH_EXPORT double gemhook_pool_acquire(gemhook_pool* p, int slot, double overuse_ms, double burst_ms) {
+  Slot& me = p->r->slots[slot];
+  p->lock();
+  request_locked(p, slot, p->now_ms(), overuse_ms, burst_ms);
+  p->unlock();
+  for (;;) {
+    int who = -1;
+    double q = 0, sleep_ms = 0;
+    p->lock();
+    int rc = p->schedule_locked(p->now_ms(), &who, &q, &sleep_ms);
+    p->unlock();
+    if (rc == 1 && who != slot) futex(&p->r->slots[who].state, FUTEX_WAKE, 1, nullptr);  // wake the winner
+    if (me.state.load(std::memory_order_acquire) == ST_GRANTED) {
+      double got = me.granted_quota;
+      me.state.store(ST_IDLE, std::memory_order_release);
+      return got;
+    }
+    // someone else holds the token, or everyone is throttled: sleep on our own slot word until the hint
+    // expires or a granter wakes us.  Short waits spin (no context switch on a quick hand-over).
+    double wait_ms = (rc == 0 || rc == -2) ? sleep_ms : 0.2;
+    if (wait_ms < 0.05) {
+      for (int i = 0; i < 200 && me.state.load(std::memory_order_acquire) != ST_GRANTED; i++) __builtin_ia32_pause();
+      continue;
+    }
+    if (wait_ms > 50.0) wait_ms = 50.0;  // re-evaluate periodically (config reloads, dead holders)
+    struct timespec ts;
+    ts.tv_sec = (time_t)(wait_ms / 1e3);
+    ts.tv_nsec = (long)((wait_ms - ts.tv_sec * 1e3) * 1e6);
+    futex(&me.state, FUTEX_WAIT, ST_WAITING, &ts);
+  }
+}
+
+// ---- gpu_mem cap: integer exact, requested bytes (hook.cpp:590-617, pod-manager.cpp:295-313) -----------
+GH_EXPORT int gemhook_pool_mem_reserve(gemhook_pool* p, int slot, uint64_t bytes) {
+  Slot& s = p->r->slots[slot];
+  uint64_t used = s.mem_used.load(std::memory_order_relaxed);
+  for (;;) {
+    // reference pre-hook: remain = limit - used (size_t arithmetic); deny iff bytes > remain
+    uint64_t remain = s.mem_limit - used;
+    if (bytes > remain) return 0;
+    if (s.mem_used.compare_exchange_weak(used, used + bytes, std::memory_order_acq_rel)) return 1;
+  }
+}
+GH_EXPORT void gemhook_pool_mem_release(gemhook_pool* p, int slot, uint64_t bytes) {
+  p->r->slots[slot].mem_used.fetch_sub(bytes, std::memory_order_acq_rel);
+}
+GH_EXPORT void gemhook_pool_mem_info(const gemhook_pool* p, int slot, uint64_t* used, uint64_t* limit) {
+  if (used) *used = p->r->slots[slot].mem_used.load(std::memory_order_acquire);
+  if (limit) *limit = p->r->slots[slot].mem_limit;
+}
+void gh_pool_publish_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches) {
+  p->r->slots[slot].gpu_ns.store(gpu_ns, std::memory_order_relaxed);
+  p->r->slots[slot].launches.store(launches, std::memory_order_relaxed);
+}
+
+// hook.cpp:638-680: bytes charged for arrays.  CUarray_format: U8 0x01, U16 0x02, U32 0x03, S8 0x08,
+// S16 0x09, S32 0x0a, HALF 0x10, FLOAT 0x20; any other format is outside the reference's switch
+// (undefined there) and is charged 0 bytes here.
+GH_EXPORT uint64_t gemhook_array_bytes(uint64_t w, uint64_t h, uint64_t d, uint32_t channels, uint32_t format, int is3d) {
+  uint64_t fs;
+  switch (format) {
+    case 0x01: case 0x08: fs = 1; break;
+    case 0x02: case 0x09: case 0x10: fs = 2; break;
+    case 0x03: case 0x0a: case 0x20: fs = 4; break;
+    default: fs = 0; break;
+  }
+  return (is3d ? w * h * d * channels : w * h * channels) * fs;
+}

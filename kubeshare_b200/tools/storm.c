@@ -1,0 +1,301 @@
+/*
+ * gem-storm -- the synthetic CUDA client of the benchmark and of the LD_PRELOAD tests.
+ * Driver API only (the thinnest possible un-hooked launch path, so hook overhead is measured against
+ * the hardest baseline).  Workloads follow SURVEY.md 8(d):
+ *
+ *   storm    W warm-up + K timed steps; a step = B launches of noop<<<1,32>>> on the default stream with
+ *            cuCtxSynchronize every S launches                                          (configs 1, 2)
+ *   bursty   R rounds of { L ~ U{16..4096} launches of a ~5 us spin kernel; sync; sleep Exp(2 ms) },
+ *            seed 0xB200                                                                (config 3)
+ *   memsweep cudaMalloc-style sweep: 256 MiB x i cumulative toward --sweep-bytes, then 1000 odd-sized
+ *            allocations U[1, 64 MiB], seed 4                                           (config 4)
+ *   mnist    iterations of 100 conv launches (N=64, 1->32->64 channels, 28x28, 3x3) + one DtoH (config 5)
+ *   probe    host cost of the primitives the hook builds on (launch, event record, elapsed, stamp)
+ *
+ * Output: ONE JSON object on stdout (or --out FILE).  Timing: CUDA events around the timed region on the
+ * stream used (device time) AND CLOCK_MONOTONIC around the same region (host wall time).
+ */
+#define _GNU_SOURCE
+#include <cuda.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+extern const unsigned char _binary_storm_kernels_cubin_start[];
+
+#define CK(x)                                                                 \
+  do {                                                                        \
+    CUresult _r = (x);                                                        \
+    if (_r != CUDA_SUCCESS) {                                                 \
+      const char* _s = NULL;                                                  \
+      cuGetErrorString(_r, &_s);                                              \
+      fprintf(stderr, "gem-storm: %s -> %d (%s)\n", #x, (int)_r, _s ? _s : "?"); \
+      exit(3);                                                                \
+    }                                                                         \
+  } while (0)
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
+static uint64_t rng_state;
+static uint32_t rng_u32(void) {  /* splitmix64 */
+  uint64_t z = (rng_state += 0x9e3779b97f4a7c15ULL);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return (uint32_t)((z ^ (z >> 31)) >> 16);
+}
+static double rng_unit(void) { return (rng_u32() + 0.5) / 4294967296.0; }
+
+/* file barrier so that co-resident clients enter the timed region together */
+static void barrier(const char* dir, int id, int n, const char* tag) {
+  if (!dir || n <= 1) return;
+  char path[600];
+  snprintf(path, sizeof(path), "%s/%s.%d", dir, tag, id);
+  FILE* f = fopen(path, "w");
+  if (f) fclose(f);
+  for (;;) {
+    int seen = 0;
+    for (int i = 0; i < n; i++) {
+      struct stat st;
+      snprintf(path, sizeof(path), "%s/%s.%d", dir, tag, i);
+      if (stat(path, &st) == 0) seen++;
+    }
+    if (seen == n) return;
+    usleep(500);
+  }
+}
+
+static CUfunction f_noop, f_spin, f_conv;
+
+int main(int argc, char** argv) {
+  const char* mode = "storm";
+  long step_launches = 65536, sync_every = 1024, steps = 16, warmup = 3, rounds = 2000;
+  double spin_us = 5.0, sleep_mean_ms = 2.0;
+  unsigned long long sweep_bytes = 40ULL << 30;
+  const char* out_path = NULL;
+  const char* barrier_dir = NULL;
+  int client_id = 0, nclients = 1, iters = 20;
+  for (int i = 1; i < argc; i++) {
+    if (!strcmp(argv[i], "--mode") && i + 1 < argc) mode = argv[++i];
+    else if (!strcmp(argv[i], "--step-launches") && i + 1 < argc) step_launches = atol(argv[++i]);
+    else if (!strcmp(argv[i], "--sync-every") && i + 1 < argc) sync_every = atol(argv[++i]);
+    else if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atol(argv[++i]);
+    else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atol(argv[++i]);
+    else if (!strcmp(argv[i], "--rounds") && i + 1 < argc) rounds = atol(argv[++i]);
+    else if (!strcmp(argv[i], "--spin-us") && i + 1 < argc) spin_us = atof(argv[++i]);
+    else if (!strcmp(argv[i], "--sleep-mean-ms") && i + 1 < argc) sleep_mean_ms = atof(argv[++i]);
+    else if (!strcmp(argv[i], "--sweep-bytes") && i + 1 < argc) sweep_bytes = strtoull(argv[++i], NULL, 0);
+    else if (!strcmp(argv[i], "--out") && i + 1 < argc) out_path = argv[++i];
+    else if (!strcmp(argv[i], "--barrier-dir") && i + 1 < argc) barrier_dir = argv[++i];
+    else if (!strcmp(argv[i], "--client-id") && i + 1 < argc) client_id = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--nclients") && i + 1 < argc) nclients = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--iters") && i + 1 < argc) iters = atoi(argv[++i]);
+    else {
+      fprintf(stderr, "gem-storm: unknown argument %s\n", argv[i]);
+      return 2;
+    }
+  }
+  FILE* out = out_path ? fopen(out_path, "w") : stdout;
+  if (!out) return 2;
+
+  CUdevice dev;
+  CUcontext ctx;
+  CUmodule mod;
+  CK(cuInit(0));
+  CK(cuDeviceGet(&dev, 0));
+  CK(cuDevicePrimaryCtxRetain(&ctx, dev));
+  CK(cuCtxSetCurrent(ctx));
+  CK(cuModuleLoadData(&mod, _binary_storm_kernels_cubin_start));
+  CK(cuModuleGetFunction(&f_noop, mod, "noop"));
+  CK(cuModuleGetFunction(&f_spin, mod, "spin"));
+  CK(cuModuleGetFunction(&f_conv, mod, "conv3x3"));
+  CUevent e0, e1;
+  CK(cuEventCreate(&e0, CU_EVENT_DEFAULT));
+  CK(cuEventCreate(&e1, CU_EVENT_DEFAULT));
+
+  if (!strcmp(mode, "storm")) {
+    /* un-timed warm-up steps, barrier, then exactly K timed steps */
+    for (long s = 0; s < warmup; s++) {
+      for (long i = 1; i <= step_launches; i++) {
+        CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+        if (i % sync_every == 0) CK(cuCtxSynchronize());
+      }
+      CK(cuCtxSynchronize());
+    }
+    barrier(barrier_dir, client_id, nclients, "ready");
+    double* step_s = (double*)calloc((size_t)steps + 1, sizeof(double));
+    CK(cuCtxSynchronize());
+    double t0 = now_s();
+    CK(cuEventRecord(e0, NULL));
+    for (long s = 0; s < steps; s++) {
+      double ts = now_s();
+      for (long i = 1; i <= step_launches; i++) {
+        CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+        if (i % sync_every == 0) CK(cuCtxSynchronize());
+      }
+      CK(cuCtxSynchronize());
+      step_s[s] = now_s() - ts;
+    }
+    CK(cuEventRecord(e1, NULL));
+    CK(cuEventSynchronize(e1));
+    double t1 = now_s();
+    float ev_ms = 0;
+    CK(cuEventElapsedTime(&ev_ms, e0, e1));
+    fprintf(out,
+            "{\"mode\": \"storm\", \"client\": %d, \"launches\": %ld, \"steps\": %ld, \"warmup\": %ld, "
+            "\"step_launches\": %ld, \"sync_every\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f, \"t0\": %.9f, "
+            "\"t1\": %.9f, \"step_s\": [",
+            client_id, steps * step_launches, steps, warmup, step_launches, sync_every, t1 - t0, ev_ms, t0, t1);
+    for (long s = 0; s < steps; s++) fprintf(out, "%s%.9f", s ? ", " : "", step_s[s]);
+    fprintf(out, "]}\n");
+  } else if (!strcmp(mode, "bursty")) {
+    rng_state = 0xB200ULL + (uint64_t)client_id;
+    unsigned long long ns = (unsigned long long)(spin_us * 1000.0);
+    void* args[] = {&ns};
+    long total = 0;
+    barrier(barrier_dir, client_id, nclients, "ready");
+    double t0 = now_s();
+    CK(cuEventRecord(e0, NULL));
+    for (long r = 0; r < rounds; r++) {
+      long L = 16 + (long)(rng_u32() % (4096 - 16 + 1));
+      for (long i = 0; i < L; i++) CK(cuLaunchKernel(f_spin, 1, 1, 1, 32, 1, 1, 0, NULL, args, NULL));
+      total += L;
+      CK(cuCtxSynchronize());
+      double sl = -log(rng_unit()) * sleep_mean_ms;
+      struct timespec ts = {(time_t)(sl / 1e3), (long)(fmod(sl, 1e3) * 1e6)};
+      nanosleep(&ts, NULL);
+    }
+    CK(cuEventRecord(e1, NULL));
+    CK(cuEventSynchronize(e1));
+    double t1 = now_s();
+    float ev_ms = 0;
+    CK(cuEventElapsedTime(&ev_ms, e0, e1));
+    fprintf(out, "{\"mode\": \"bursty\", \"client\": %d, \"rounds\": %ld, \"launches\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f}\n",
+            client_id, rounds, total, t1 - t0, ev_ms);
+  } else if (!strcmp(mode, "memsweep")) {
+    /* sweep 1: s_i = 256 MiB * i, cumulative, until the running total would pass sweep_bytes */
+    fprintf(out, "{\"mode\": \"memsweep\", \"sweep1\": [");
+    unsigned long long total = 0;
+    long first_fail = -1;
+    CUdeviceptr held[512];
+    int nheld = 0;
+    for (long i = 1; total < sweep_bytes && i < 512; i++) {
+      size_t sz = (size_t)(256ULL << 20) * (size_t)i;
+      CUdeviceptr p = 0;
+      CUresult r = cuMemAlloc(&p, sz);
+      size_t fr = 0, tot = 0;
+      cuMemGetInfo(&fr, &tot);
+      fprintf(out, "%s{\"i\": %ld, \"bytes\": %zu, \"rc\": %d, \"free\": %zu, \"total\": %zu}", i > 1 ? ", " : "", i, sz, (int)r, fr, tot);
+      if (r == CUDA_SUCCESS) {
+        held[nheld++] = p;
+        total += sz;
+      } else {
+        if (first_fail < 0) first_fail = i;
+        if (r != CUDA_ERROR_OUT_OF_MEMORY) break;
+        total += sz; /* keep sweeping "toward 40 GiB" as the config says */
+      }
+    }
+    for (int i = 0; i < nheld; i++) cuMemFree(held[i]);
+    size_t fr = 0, tot = 0;
+    cuMemGetInfo(&fr, &tot);
+    fprintf(out, "], \"first_fail\": %ld, \"free_after_release\": %zu, \"total\": %zu, \"sweep2\": [", first_fail, fr, tot);
+    /* sweep 2: 1000 odd-sized allocations, never freed until the end */
+    rng_state = 4;
+    CUdeviceptr* h2 = (CUdeviceptr*)calloc(1000, sizeof(CUdeviceptr));
+    int n2 = 0;
+    for (int i = 0; i < 1000; i++) {
+      size_t sz = 1 + (size_t)(((uint64_t)rng_u32() << 10 | (rng_u32() & 1023)) % (64ULL << 20));
+      CUdeviceptr p = 0;
+      CUresult r = cuMemAlloc(&p, sz);
+      cuMemGetInfo(&fr, &tot);
+      fprintf(out, "%s[%zu, %d, %zu]", i ? ", " : "", sz, (int)r, fr);
+      if (r == CUDA_SUCCESS) h2[n2++] = p;
+    }
+    for (int i = 0; i < n2; i++) cuMemFree(h2[i]);
+    cuMemGetInfo(&fr, &tot);
+    fprintf(out, "], \"free_end\": %zu}\n", fr);
+  } else if (!strcmp(mode, "mnist")) {
+    const int N = 64;
+    CUdeviceptr d_in, d_w1, d_a1, d_w2, d_a2;
+    CK(cuMemAlloc(&d_in, (size_t)N * 1 * 784 * 4));
+    CK(cuMemAlloc(&d_w1, 32 * 1 * 9 * 4));
+    CK(cuMemAlloc(&d_a1, (size_t)N * 32 * 784 * 4));
+    CK(cuMemAlloc(&d_w2, 64 * 32 * 9 * 4));
+    CK(cuMemAlloc(&d_a2, (size_t)N * 64 * 784 * 4));
+    CK(cuMemsetD8(d_in, 0, (size_t)N * 784 * 4));
+    CK(cuMemsetD8(d_w1, 0, 32 * 9 * 4));
+    CK(cuMemsetD8(d_w2, 0, 64 * 32 * 9 * 4));
+    float* host = (float*)malloc(64 * 4);
+    int c1i = 1, c1o = 32, c2i = 32, c2o = 64;
+    void* a1[] = {&d_in, &d_w1, &d_a1, &c1i, &c1o};
+    void* a2[] = {&d_a1, &d_w2, &d_a2, &c2i, &c2o};
+    barrier(barrier_dir, client_id, nclients, "ready");
+    long launches = 0;
+    double t0 = now_s();
+    CK(cuEventRecord(e0, NULL));
+    for (int it = 0; it < iters; it++) {
+      for (int k = 0; k < 50; k++) {
+        CK(cuLaunchKernel(f_conv, 32, N, 1, 28, 28, 1, 0, NULL, a1, NULL));
+        CK(cuLaunchKernel(f_conv, 64, N, 1, 28, 28, 1, 0, NULL, a2, NULL));
+        launches += 2;
+      }
+      CK(cuMemcpyDtoH(host, d_a2, 64 * 4));
+    }
+    CK(cuEventRecord(e1, NULL));
+    CK(cuEventSynchronize(e1));
+    double t1 = now_s();
+    float ev_ms = 0;
+    CK(cuEventElapsedTime(&ev_ms, e0, e1));
+    fprintf(out, "{\"mode\": \"mnist\", \"client\": %d, \"iters\": %d, \"launches\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f}\n",
+            client_id, iters, launches, t1 - t0, ev_ms);
+  } else if (!strcmp(mode, "probe")) {
+    /* host cost (ns) of the building blocks; medians would be nicer, means over 20k are stable enough */
+    const int N = 20000;
+    for (int i = 0; i < 2000; i++) CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+    CK(cuCtxSynchronize());
+    double t = now_s();
+    for (int i = 0; i < N; i++) {
+      CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+      if ((i & 1023) == 1023) CK(cuCtxSynchronize());
+    }
+    CK(cuCtxSynchronize());
+    double launch_ns = (now_s() - t) / N * 1e9;
+    CUevent ev[64];
+    for (int i = 0; i < 64; i++) CK(cuEventCreate(&ev[i], CU_EVENT_DEFAULT));
+    t = now_s();
+    for (int i = 0; i < N; i++) CK(cuEventRecord(ev[i & 63], NULL));
+    double rec_ns = (now_s() - t) / N * 1e9;
+    CK(cuCtxSynchronize());
+    float ms;
+    t = now_s();
+    for (int i = 0; i < N; i++) cuEventElapsedTime(&ms, ev[i & 31], ev[32 + (i & 31)]);
+    double el_ns = (now_s() - t) / N * 1e9;
+    t = now_s();
+    for (int i = 0; i < N; i++) cuEventQuery(ev[i & 63]);
+    double q_ns = (now_s() - t) / N * 1e9;
+    t = now_s();
+    for (int i = 0; i < 200; i++) CK(cuCtxSynchronize());
+    double sync_ns = (now_s() - t) / 200 * 1e9;
+    struct timespec ts;
+    t = now_s();
+    for (int i = 0; i < 1000000; i++) clock_gettime(CLOCK_MONOTONIC, &ts);
+    double clk_ns = (now_s() - t) / 1e6 * 1e9;
+    fprintf(out,
+            "{\"mode\": \"probe\", \"launch_ns\": %.1f, \"event_record_ns\": %.1f, \"event_elapsed_ns\": %.1f, "
+            "\"event_query_ns\": %.1f, \"idle_ctx_sync_ns\": %.1f, \"clock_gettime_ns\": %.1f, \"cpus\": %ld}\n",
+            launch_ns, rec_ns, el_ns, q_ns, sync_ns, clk_ns, sysconf(_SC_NPROCESSORS_ONLN));
+  } else {
+    fprintf(stderr, "gem-storm: unknown mode %s\n", mode);
+    return 2;
+  }
+  if (out != stdout) fclose(out);
+  return 0;
+}

@@ -1,0 +1,118 @@
+"""GPU parity of the sm_100a accounting reduction against the CPU oracle -- bit-exact (u64 sums).
+
+Calls go through the C ABI (include/gemhook.h 2d) of libgemhook.so.1; torch only supplies the CUDA
+context and device memory.
+"""
+import numpy as np
+import pytest
+
+import kubeshare_b200 as kb
+import orc
+
+pytestmark = pytest.mark.gpu
+
+REC = np.dtype([("slot", "<u4"), ("launches", "<u4"), ("elapsed_ns", "<u8")])
+
+
+def make_records(n, nslots, seed, out_of_range=0.05, big=False):
+    rng = np.random.default_rng(seed)
+    r = np.zeros(n, REC)
+    r["slot"] = rng.integers(0, nslots, n, dtype=np.uint32)
+    if out_of_range and n:
+        bad = rng.random(n) < out_of_range
+        r["slot"][bad] = rng.integers(nslots, 2**32, int(bad.sum()), dtype=np.uint64).astype(np.uint32)
+    r["launches"] = rng.integers(0, 2**32 if big else 4097, n, dtype=np.uint64).astype(np.uint32)
+    r["elapsed_ns"] = rng.integers(0, 2**62 if big else 50_000_000, n, dtype=np.uint64)
+    return r
+
+
+def oracle(L, r, nslots):
+    ns, la, rc = orc.acct_reduce(L, r, nslots)
+    return np.stack([ns, la, rc], axis=1)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available()
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")  # make the primary context current on this thread
+    return torch
+
+
+@pytest.fixture(scope="module")
+def OL():
+    return orc.load()
+
+
+@pytest.mark.parametrize("nslots", [1, 2, 8, 21, 64])
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 255, 256, 257, 4097, 100_003, 1 << 20])
+def test_reduce_host_matches_oracle(torch_cuda, OL, nslots, n):
+    a = kb.Acct(nslots, ring_capacity=1 << 18)  # n > capacity exercises the chunked path
+    try:
+        r = make_records(n, nslots, seed=n * 131 + nslots)
+        got = a.reduce_host(r)
+        assert (got == oracle(OL, r, nslots)).all()
+        # running totals: a second batch accumulates on top
+        r2 = make_records(n // 2 + 3, nslots, seed=7 * n + nslots, big=True)
+        got2 = a.reduce_host(r2)
+        want2 = oracle(OL, r, nslots) + oracle(OL, r2, nslots)  # uint64 wrap-around is part of the contract
+        assert (got2 == want2).all()
+    finally:
+        a.close()
+
+
+def test_reduce_device_resident_and_page(torch_cuda, OL):
+    torch = torch_cuda
+    nslots, n = 4, (1 << 22) + 77
+    r = make_records(n, nslots, seed=99)
+    d = torch.from_numpy(r.view(np.uint8).reshape(-1).copy()).cuda()
+    a = kb.Acct(nslots)
+    try:
+        ms = a.reduce_device(d.data_ptr(), n, timed=True)
+        assert ms > 0
+        tot, epoch = a.totals()
+        assert epoch == 1
+        assert (tot == oracle(OL, r, nslots)).all()
+        a.reset()
+        tot, _ = a.totals()
+        assert (tot == 0).all()
+        # linearity / split invariance at a size the oracle would take long on: reduce halves separately
+        a.reduce_device(d.data_ptr(), n // 2)
+        a.reduce_device(d.data_ptr() + (n // 2) * 16, n - n // 2)
+        tot2, epoch2 = a.totals()
+        assert (tot2 == oracle(OL, r, nslots)).all()
+        assert a.kernel_launches >= 4
+    finally:
+        a.close()
+
+
+def test_full_size_properties(torch_cuda):
+    """BASELINE-size ring (2^26 records = 1 GiB): constant records make the answer closed-form."""
+    torch = torch_cuda
+    n, nslots = 1 << 26, 8
+    rec = torch.empty((n, 4), dtype=torch.int32, device="cuda")
+    idx = torch.arange(n, device="cuda", dtype=torch.int64)
+    rec[:, 0] = (idx % nslots).to(torch.int32)          # slot
+    rec[:, 1] = 3                                        # launches
+    rec[:, 2] = 1000                                     # elapsed_ns low word
+    rec[:, 3] = 0                                        # high word
+    a = kb.Acct(nslots)
+    try:
+        a.reduce_device(rec.data_ptr(), n)
+        tot, _ = a.totals()
+        per = n // nslots
+        assert (tot[:, 0] == per * 1000).all() and (tot[:, 1] == per * 3).all() and (tot[:, 2] == per).all()
+    finally:
+        a.close()
+
+
+def test_misaligned_pointer_is_rejected(torch_cuda):
+    a = kb.Acct(2)
+    try:
+        t = torch_cuda.zeros(64, dtype=torch_cuda.uint8, device="cuda")
+        with pytest.raises(RuntimeError):
+            a.reduce_device(t.data_ptr() + 8, 1)
+    finally:
+        a.close()
