@@ -112,6 +112,21 @@ def quota_text(nclients):
     return "%d\n%s\n" % (nclients, "\n".join(rows))
 
 
+def free_ports(n):
+    """n distinct currently-free TCP ports (fresh per run: gem-schd binds without SO_REUSEADDR)."""
+    import socket
+
+    socks = []
+    for _ in range(n):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        socks.append(s)
+    ports = [s.getsockname()[1] for s in socks]
+    for s in socks:
+        s.close()
+    return ports
+
+
 def pin(core):
     def f():
         try:
@@ -138,15 +153,13 @@ def run_clients(nclients, steps, warmup, gpu, mode, core_base, step_launches=STE
             os.makedirs("/kubeshare/log", exist_ok=True)
             with open("/kubeshare/library/schedulerIP.txt", "w") as f:
                 f.write("127.0.0.1\n")
-            sport = 49000 + (os.getpid() % 500) * 20 + gpu * 1000 % 15000
-            sport = 20000 + (os.getpid() * 37 + gpu * 991) % 20000
+            sport = free_ports(1)[0]
             schd = sp.Popen([os.path.join(REFDIR, "gem-schd"), "-p", tmp, "-f", "quota.txt", "-P", str(sport), "-q", "300",
                              "-m", "20", "-w", "10000"], stdout=sp.DEVNULL, stderr=sp.DEVNULL,
                             preexec_fn=pin(core_base + 2 * nclients))
             daemons.append(schd)
             time.sleep(0.4)
-            for i in range(nclients):
-                port = sport + 1 + i
+            for i, port in enumerate(free_ports(nclients)):
                 ports.append(port)
                 e = dict(env0, POD_NAME="bench/c%d" % i, POD_MANAGER_PORT=str(port), SCHEDULER_IP="127.0.0.1",
                          SCHEDULER_PORT=str(sport))
@@ -278,6 +291,7 @@ def main():
     ap.add_argument("--clients", default="1,2,4,8", help="co-resident client counts to sweep")
     ap.add_argument("--headline-clients", type=int, default=2)
     ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--only-roofline", action="store_true", help="run just the accounting-kernel leg (for ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
         log("warm-up raised to 3 (timing rules)")
@@ -307,6 +321,11 @@ def main():
         ge.build()
     if dist:
         dist.barrier()
+
+    if args.only_roofline:
+        os.environ["CUDA_VISIBLE_DEVICES"] = str(gpu)
+        print(json.dumps(roofline_kernel(args.steps, args.warmup)))
+        return
 
     if args.impl == "reference" and not os.path.exists(os.path.join(REFDIR, "libgemhook_ref.so.1")):
         if rank == 0:
@@ -398,6 +417,8 @@ def main():
         "e2e": {"value": lh / hh, "unit": "launches/s",
                 "h2d_bytes_per_step": (16 * segments // max(1, (args.steps + args.warmup))) if mode == "ours" else 0,
                 "d2h_bytes_per_step": (acct_kernels * (32 + 24 * hc) // max(1, (args.steps + args.warmup))) if mode == "ours" else 0},
+        "hook_stats": {str(c): [{k: s.get(k) for k in ("token_requests", "token_wait_ms", "slow_path", "segments", "acct_kernels", "gpu_ns", "accumulated_token_ms", "quota_ms")}
+                                 for r in allr for s in r[c]["hooked"].get("stats", [])] for c in sweep},
         "gpu_launches": int(acct_kernels + (roof or {}).get("kernel_launches", 0)) if mode == "ours" else 0,
         "clocks": clocks, "host": {"cpus": ncpu, "client_cores": "one pinned core per client, daemons on their own cores"},
         "wall_s": time.time() - t_start,

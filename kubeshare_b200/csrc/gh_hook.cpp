@@ -503,6 +503,7 @@ void gh_register_exit_hook(void);
 static void write_stats_file(void) {
   const char* pat = getenv("GEMHOOK_STATS_FILE");
   gh_live* L = g_live;
+  if (L && L->enabled && L->pool) gemhook_pool_release(L->pool, L->slot);  // do not make peers wait for a timeout
   if (!pat || !*pat || !L) return;
   gemhook_flush();
   gemhook_stats s;

@@ -506,6 +506,32 @@ GH_EXPORT double gemhook_pool_acquire(gemhook_pool* p, int slot, double overuse_
   }
 }
 
+// A client that is going away (process exit) hands its token back instead of letting the scheduler wait
+// for the quota to time out (the reference can only time out: scheduler.cpp:507-510).  The ledger entry is
+// closed exactly as a returning client's would be (update_return_time with zero overuse).
+GH_EXPORT void gemhook_pool_release(gemhook_pool* p, int slot) {
+  if (!p || slot < 0) return;
+  p->lock();
+  Header& h = p->r->h;
+  double now = p->now_ms();
+  int who = -1;
+  if (h.holder == slot) {
+    for (uint32_t i = h.ledger_len; i-- > 0;)
+      if (p->r->ledger[i].slot == slot) {
+        p->r->ledger[i].end = std::min(now, p->r->ledger[i].end);
+        break;
+      }
+    Slot& s = p->r->slots[slot];
+    if (s.grants) s.last_end = std::min(now, s.last_end);
+    h.holder = -1;
+    double q, sl;
+    p->schedule_locked(now, &who, &q, &sl);
+  }
+  if (p->r->slots[slot].state.load() == ST_WAITING) p->r->slots[slot].state.store(ST_IDLE);
+  p->unlock();
+  if (who >= 0) futex(&p->r->slots[who].state, FUTEX_WAKE, 1, nullptr);
+}
+
 // ---- gpu_mem cap: integer exact, requested bytes (hook.cpp:590-617, pod-manager.cpp:295-313) -----------
 GH_EXPORT int gemhook_pool_mem_reserve(gemhook_pool* p, int slot, uint64_t bytes) {
   Slot& s = p->r->slots[slot];
