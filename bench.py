@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 STORM = os.path.join(ROOT, "kubeshare_b200", "bin", "gem-storm")
 HOOK = os.path.join(ROOT, "kubeshare_b200", "lib", "libgemhook.so.1")
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
-STEP_LAUNCHES = 65536
+STEP_LAUNCHES = int(os.environ.get("GEMBENCH_STEP_LAUNCHES", "65536"))  # override only for the CPU stub tests
 SYNC_EVERY = 1024
 GIB8 = 8589934592
 
@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--clients", default="1,2,4,8", help="co-resident client counts to sweep")
     ap.add_argument("--headline-clients", type=int, default=2)
     ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--skip-baseline", action="store_true", help="skip the reference cpu_baseline leg")
     ap.add_argument("--only-roofline", action="store_true", help="run just the accounting-kernel leg (for ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -361,7 +362,7 @@ def main():
             w0 = time.time()
             roof = roofline_kernel(args.steps, args.warmup)
             windows.append((w0, time.time()))
-        if os.path.exists(os.path.join(REFDIR, "libgemhook_ref.so.1")):
+        if os.path.exists(os.path.join(REFDIR, "libgemhook_ref.so.1")) and not args.skip_baseline:
             try:  # bounded sample of the same workload through the reference stack
                 k_ref = min(args.steps, 4)
                 cpu_ref = run_clients(args.headline_clients, k_ref, 3, gpu, "reference", core_base)

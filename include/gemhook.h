@@ -154,6 +154,8 @@ double gemhook_pool_accumulated_ms(const gemhook_pool *, int slot);
 double gemhook_pool_acquire(gemhook_pool *, int slot, double overuse_ms, double burst_ms);
 /* hand an outstanding token back early (client exit); the next waiter is scheduled immediately. */
 void gemhook_pool_release(gemhook_pool *, int slot);
+/* declare the outstanding token timed out (scheduler.cpp:507-510) without touching the ledger. */
+void gemhook_pool_expire_token(gemhook_pool *);
 
 /* gpu_mem cap on the pool slot (hook.cpp:590-617, pod-manager.cpp:295-313): uint64, requested bytes. */
 int gemhook_pool_mem_reserve(gemhook_pool *, int slot, uint64_t bytes);   /* 1 ok, 0 over the cap */

@@ -532,6 +532,16 @@ GH_EXPORT void gemhook_pool_release(gemhook_pool* p, int slot) {
   if (who >= 0) futex(&p->r->slots[who].state, FUTEX_WAKE, 1, nullptr);
 }
 
+// The outstanding token is declared timed out (what gem-schd concludes when its timedwait on the holder
+// returns ETIMEDOUT, scheduler.cpp:507-510) without touching the ledger: trace replays use it to decouple
+// decisions from wall time, a node agent can use it to revoke the token of a client it knows is dead.
+GH_EXPORT void gemhook_pool_expire_token(gemhook_pool* p) {
+  if (!p) return;
+  p->lock();
+  p->r->h.holder = -1;
+  p->unlock();
+}
+
 // ---- gpu_mem cap: integer exact, requested bytes (hook.cpp:590-617, pod-manager.cpp:295-313) -----------
 GH_EXPORT int gemhook_pool_mem_reserve(gemhook_pool* p, int slot, uint64_t bytes) {
   Slot& s = p->r->slots[slot];

@@ -17,6 +17,7 @@
  */
 #define _GNU_SOURCE
 #include <cuda.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -256,6 +257,37 @@ int main(int argc, char** argv) {
     CK(cuEventElapsedTime(&ev_ms, e0, e1));
     fprintf(out, "{\"mode\": \"mnist\", \"client\": %d, \"iters\": %d, \"launches\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f}\n",
             client_id, iters, launches, t1 - t0, ev_ms);
+  } else if (!strcmp(mode, "resolve")) {
+    /* the three ways an application reaches the driver: direct symbol, dlsym(), cuGetProcAddress */
+    typedef CUresult (*launch_t)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                 CUstream, void**, void**);
+    typedef CUresult (*alloc_t)(CUdeviceptr*, size_t);
+    typedef CUresult (*free_t)(CUdeviceptr);
+    void* h = dlopen("libcuda.so.1", RTLD_NOW);
+    launch_t via_dlsym = (launch_t)dlsym(h, "cuLaunchKernel");
+    alloc_t alloc_dlsym = (alloc_t)dlsym(h, "cuMemAlloc_v2");
+    launch_t via_gpa = NULL;
+    alloc_t alloc_gpa = NULL;
+    free_t free_gpa = NULL;
+    CUdriverProcAddressQueryResult st;
+    CK(cuGetProcAddress("cuLaunchKernel", (void**)&via_gpa, 12000, CU_GET_PROC_ADDRESS_DEFAULT, &st));
+    CK(cuGetProcAddress("cuMemAlloc", (void**)&alloc_gpa, 12000, CU_GET_PROC_ADDRESS_DEFAULT, &st));
+    CK(cuGetProcAddress("cuMemFree", (void**)&free_gpa, 12000, CU_GET_PROC_ADDRESS_DEFAULT, &st));
+    void* gpa_again = NULL; /* cudart asks the driver for cuGetProcAddress itself */
+    CK(cuGetProcAddress("cuGetProcAddress", &gpa_again, 12000, CU_GET_PROC_ADDRESS_DEFAULT, &st));
+    for (int i = 0; i < 10; i++) CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+    for (int i = 0; i < 10; i++) CK(via_dlsym(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+    for (int i = 0; i < 10; i++) CK(via_gpa(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+    CK(cuCtxSynchronize());
+    CUdeviceptr a = 0, b = 0, c = 0;
+    CUresult r1 = cuMemAlloc(&a, 1000), r2 = alloc_dlsym(&b, 2000), r3 = alloc_gpa(&c, 3000);
+    size_t fr = 0, tot = 0;
+    cuMemGetInfo(&fr, &tot);
+    fprintf(out, "{\"mode\": \"resolve\", \"rc\": [%d, %d, %d], \"free\": %zu, \"total\": %zu, \"gpa_is_hooked\": %d}\n",
+            (int)r1, (int)r2, (int)r3, fr, tot, gpa_again != NULL);
+    free_gpa(c);
+    cuMemFree(b);
+    cuMemFree(a);
   } else if (!strcmp(mode, "probe")) {
     /* host cost (ns) of the building blocks; medians would be nicer, means over 20k are stable enough */
     const int N = 20000;

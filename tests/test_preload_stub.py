@@ -1,0 +1,294 @@
+"""CPU: libgemhook.so.1 under LD_PRELOAD against the stub driver (tests/stub/libcuda.so.1).
+
+BASELINE.json configs[0] (dry run: 1000 launches, quota-file parse), the three binding paths (direct
+symbol, dlsym, cuGetProcAddress), the token protocol on the wire -- against a scripted fake pod manager
+AND against the live reference gem-pmgr + gem-schd --, the gpu_mem cap (config 4 sweep, bit-exact vs the
+oracle rule) and two co-resident clients arbitrating through the shared credit pool.
+"""
+import json
+import os
+import socket
+import subprocess as sp
+import tempfile
+import threading
+import time
+
+import pytest
+
+import kubeshare_b200 as kb
+import orc
+import wireproto as wp
+
+REF = os.path.join(kb.ROOT, "oracle", "_ref")
+HAVE_REF = os.path.exists(os.path.join(REF, "gem-schd")) and os.path.exists(os.path.join(REF, "gem-pmgr"))
+GIB8 = 8589934592
+
+
+def base_env(tmp, **kw):
+    env = dict(os.environ)
+    for k in list(env):
+        if k.startswith("GEMHOOK_") or k in ("LD_PRELOAD", "POD_NAME", "POD_MANAGER_PORT"):
+            env.pop(k)
+    env["LD_LIBRARY_PATH"] = kb.STUB_DIR + ":" + env.get("LD_LIBRARY_PATH", "")
+    env["STUB_REPORT"] = os.path.join(tmp, "stub.json")
+    env.update({k: str(v) for k, v in kw.items()})
+    return env
+
+
+def hooked_env(tmp, pod="bench/c0", quota="1\nbench/c0 1.0 1.0 %d\n" % GIB8, **kw):
+    with open(os.path.join(tmp, "quota.txt"), "w") as f:
+        f.write(quota)
+    return base_env(tmp, LD_PRELOAD=kb.LIB_PATH, GEMHOOK_POOL=os.path.join(tmp, "pool"),
+                    GEMHOOK_QUOTA_FILE=os.path.join(tmp, "quota.txt"), POD_NAME=pod,
+                    GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"), **kw)
+
+
+def run_storm(env, *args, timeout=60):
+    p = sp.run([kb.STORM_PATH, *map(str, args)], env=env, stdout=sp.PIPE, stderr=sp.PIPE, timeout=timeout)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    return json.loads(p.stdout)
+
+
+def stats_files(tmp):
+    out = []
+    for fn in sorted(os.listdir(tmp)):
+        if fn.startswith("stats."):
+            out.append(json.load(open(os.path.join(tmp, fn))))
+    return out
+
+
+def test_config1_dry_run_1000_launches():
+    """configs[0]: single process, hook loaded, 1000 empty-kernel launches on the CPU-side stub."""
+    with tempfile.TemporaryDirectory() as tmp:
+        env = hooked_env(tmp, GEMHOOK_DRY_RUN=1)
+        res = run_storm(env, "--mode", "storm", "--steps", 1, "--warmup", 0, "--step-launches", 1000, "--sync-every", 100)
+        assert res["launches"] == 1000
+        st = stats_files(tmp)[0]
+        stub = json.load(open(os.path.join(tmp, "stub.json")))
+        assert stub["launches"] == 1000           # every launch reached the driver exactly once
+        assert st["launches"] == 1000 and st["pod"] == "bench/c0"
+        assert st["slow_path"] == 10 and st["fast_path"] == 990   # one burst edge per sync interval
+        assert st["token_requests"] >= 2          # the discarded first token + the first launch's (hook.cpp:766-768)
+        assert st["mem_limit"] == GIB8            # quota-file parse
+        assert st["acct_kernels"] == 0 and stub["event_records"] == 2  # dry run: only the app's own two events
+
+
+def test_unknown_pod_exits_like_the_reference():
+    with tempfile.TemporaryDirectory() as tmp:
+        env = hooked_env(tmp, pod="bench/not-in-file")
+        p = sp.run([kb.STORM_PATH, "--mode", "storm", "--steps", "1", "--warmup", "0", "--step-launches", "10"], env=env,
+                   stdout=sp.PIPE, stderr=sp.PIPE, timeout=30)
+        assert p.returncode != 0 and b"not in the quota file" in p.stderr
+        env["GEMHOOK_EXIT_ON_FAILURE"] = "0"  # opt-out: run un-gated
+        res = run_storm(env, "--mode", "storm", "--steps", 1, "--warmup", 0, "--step-launches", 10)
+        assert res["launches"] == 10
+
+
+def test_all_three_binding_paths_are_hooked():
+    with tempfile.TemporaryDirectory() as tmp:
+        env = hooked_env(tmp, quota="1\nbench/c0 1.0 1.0 5000\n")
+        res = run_storm(env, "--mode", "resolve")
+        st = stats_files(tmp)[0]
+        assert st["launches"] == 30               # direct + dlsym + cuGetProcAddress_v2
+        assert res["gpa_is_hooked"] == 1
+        # cap 5000 B: 1000 ok, 2000 ok, 3000 denied (1000+2000+3000 > 5000) on the cuGetProcAddress path
+        assert res["rc"] == [0, 0, 2]             # CUDA_ERROR_OUT_OF_MEMORY == 2
+        assert (res["free"], res["total"]) == (2000, 5000)   # virtualised cuMemGetInfo
+        assert st["allocs_denied"] == 1
+
+
+def test_disabled_hook_is_transparent():
+    with tempfile.TemporaryDirectory() as tmp:
+        env = hooked_env(tmp, GEMHOOK_DISABLE=1)
+        res = run_storm(env, "--mode", "resolve")
+        assert res["rc"] == [0, 0, 0] and res["total"] == 180 << 30
+
+
+# ------------------------------------------------------------------------------------------ wire / TCP
+class FakePodManager(threading.Thread):
+    """Scripted gem-pmgr: records every raw 80-byte request, answers like pod-manager.cpp would."""
+
+    def __init__(self, limit, quota_ms):
+        super().__init__(daemon=True)
+        self.limit, self.quota_ms, self.used = limit, quota_ms, 0
+        self.raw = []
+        self.lsock = socket.socket()
+        self.lsock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        self.lsock.bind(("127.0.0.1", 0))
+        self.lsock.listen(4)
+        self.port = self.lsock.getsockname()[1]
+
+    def run(self):
+        try:
+            c, _ = self.lsock.accept()
+            while True:
+                buf = wp.recv_exact(c, wp.REQ_LEN)
+                self.raw.append(buf)
+                r = wp.unpack_request(buf)
+                if r["type"] == wp.REQ_QUOTA:
+                    c.sendall(wp.pack_response(wp.REQ_QUOTA, r["id"], quota=self.quota_ms))
+                elif r["type"] == wp.REQ_MEM_LIMIT:
+                    c.sendall(wp.pack_response(wp.REQ_MEM_LIMIT, r["id"], used=self.used, total=self.limit))
+                else:
+                    ok = 1
+                    if r["alloc"]:
+                        if self.used + r["bytes"] > self.limit:
+                            ok = 0
+                        else:
+                            self.used += r["bytes"]
+                    else:
+                        self.used -= r["bytes"]
+                    c.sendall(wp.pack_response(wp.REQ_MEM_UPDATE, r["id"], verdict=ok))
+        except (ConnectionError, OSError):
+            pass
+
+
+def test_token_protocol_bytes_on_the_wire():
+    pm = FakePodManager(limit=8192, quota_ms=50.0)
+    pm.start()
+    with tempfile.TemporaryDirectory() as tmp:
+        env = base_env(tmp, LD_PRELOAD=kb.LIB_PATH, GEMHOOK_SCHEDULER_IP="127.0.0.1", POD_MANAGER_PORT=pm.port,
+                       POD_NAME="default/mnist-pod-0123456789", GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"))
+        res = run_storm(env, "--mode", "resolve")
+        assert res["rc"] == [0, 0, 0] and res["total"] == 8192
+    reqs = [wp.unpack_request(b) for b in pm.raw]
+    assert all(len(b) == 80 for b in pm.raw)
+    assert [r["id"] for r in reqs] == list(range(len(reqs)))          # per-process counter from 0 (comm.cpp:29, 62)
+    assert all(r["name"] == "default/mnist-pod-0123456789" for r in reqs)
+    # byte-identical to the reference layout (codec pinned against the reference's own bytes in test_oracle_golden)
+    for raw, r in zip(pm.raw, reqs):
+        assert raw == wp.pack_request(r["name"], r["id"], r["type"], r.get("overuse", 0.0), r.get("burst", 0.0),
+                                      r.get("bytes", 0), r.get("alloc", 0))
+    quotas = [r for r in reqs if r["type"] == wp.REQ_QUOTA]
+    assert (quotas[0]["overuse"], quotas[0]["burst"]) == (0.0, 0.0)  # initialize(): first token, discarded
+    assert (quotas[1]["overuse"], quotas[1]["burst"]) == (0.0, 0.0)  # first launch: nothing measured yet
+    mem = [(r["bytes"], r["alloc"]) for r in reqs if r["type"] == wp.REQ_MEM_UPDATE]
+    assert mem == [(1000, 1), (2000, 1), (3000, 1), (3000, 0), (2000, 0), (1000, 0)] or \
+        mem[:3] == [(1000, 1), (2000, 1), (3000, 1)]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
+def test_drop_in_against_live_reference_daemons():
+    """Our hook speaking TCP to the UNMODIFIED gem-pmgr + gem-schd: tokens and the pod-wide memory cap."""
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "cfg.txt"), "w") as f:
+            f.write("1\nbench/c0 1.0 1.0 5000\n")
+        sport, pport = wp.free_port(), wp.free_port()
+        schd = sp.Popen([os.path.join(REF, "gem-schd"), "-p", tmp, "-f", "cfg.txt", "-P", str(sport), "-q", "300", "-m",
+                         "20", "-w", "10000"], stdout=sp.DEVNULL, stderr=sp.DEVNULL)
+        time.sleep(0.4)
+        pmgr = sp.Popen([os.path.join(REF, "gem-pmgr")], stdout=sp.DEVNULL, stderr=sp.DEVNULL,
+                        env=dict(os.environ, POD_NAME="bench/c0", POD_MANAGER_PORT=str(pport), SCHEDULER_IP="127.0.0.1",
+                                 SCHEDULER_PORT=str(sport)))
+        time.sleep(0.4)
+        try:
+            env = base_env(tmp, LD_PRELOAD=kb.LIB_PATH, GEMHOOK_SCHEDULER_IP="127.0.0.1", POD_MANAGER_PORT=pport,
+                           POD_NAME="bench/c0", GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"))
+            res = run_storm(env, "--mode", "resolve")
+            assert res["rc"] == [0, 0, 2] and (res["free"], res["total"]) == (2000, 5000)
+            res = run_storm(env, "--mode", "storm", "--steps", 2, "--warmup", 1, "--step-launches", 2000, "--sync-every", 200)
+            assert res["launches"] == 4000
+            st = stats_files(tmp)[-1]
+            assert st["token_requests"] >= 2 and st["quota_ms"] > 0
+        finally:
+            pmgr.kill()
+            schd.kill()
+            pmgr.wait()
+            schd.wait()
+
+
+# ------------------------------------------------------------------------------------------ gpu_mem cap
+def expected_sweep(limit, total_target):
+    """Oracle rule applied to gem-storm's memsweep trace: allow iff bytes <= limit - used."""
+    O = orc.load()
+    used, first_fail, rows = 0, -1, []
+    total, i = 0, 1
+    while total < total_target and i < 512:
+        sz = (256 << 20) * i
+        ok = O.orc_mem_prehook_allows(sz, used, limit)
+        if ok:
+            used += sz
+        elif first_fail < 0:
+            first_fail = i
+        rows.append((i, sz, 0 if ok else 2, limit - used))
+        total += sz
+        i += 1
+    return rows, first_fail
+
+
+def check_memsweep(res, limit):
+    rows, first_fail = expected_sweep(limit, 40 << 30)
+    got = [(r["i"], r["bytes"], r["rc"], r["free"]) for r in res["sweep1"]]
+    assert got == rows
+    assert res["first_fail"] == first_fail == 8        # 256 MiB * (1+..+7) = 7 GiB fits, +2 GiB does not
+    assert all(r["total"] == limit for r in res["sweep1"])
+    assert res["free_after_release"] == limit
+    # sweep 2: 1000 odd sizes, never freed: replay the rule on the sizes the client reports
+    O = orc.load()
+    used = 0
+    denied = 0
+    for sz, rc, free in res["sweep2"]:
+        ok = O.orc_mem_prehook_allows(sz, used, limit)
+        assert rc == (0 if ok else 2)
+        used += sz if ok else 0
+        denied += 0 if ok else 1
+        assert free == limit - used
+    assert denied > 100 and res["free_end"] == limit
+
+
+def test_config4_memory_cap_sweep_pool():
+    with tempfile.TemporaryDirectory() as tmp:
+        env = hooked_env(tmp)
+        res = run_storm(env, "--mode", "memsweep")
+        check_memsweep(res, GIB8)
+        assert stats_files(tmp)[0]["mem_used"] == 0
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
+def test_config4_memory_cap_sweep_against_live_gem_pmgr():
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "cfg.txt"), "w") as f:
+            f.write("1\nbench/c0 1.0 1.0 %d\n" % GIB8)
+        sport, pport = wp.free_port(), wp.free_port()
+        schd = sp.Popen([os.path.join(REF, "gem-schd"), "-p", tmp, "-f", "cfg.txt", "-P", str(sport)], stdout=sp.DEVNULL,
+                        stderr=sp.DEVNULL)
+        time.sleep(0.4)
+        pmgr = sp.Popen([os.path.join(REF, "gem-pmgr")], stdout=sp.DEVNULL, stderr=sp.DEVNULL,
+                        env=dict(os.environ, POD_NAME="bench/c0", POD_MANAGER_PORT=str(pport), SCHEDULER_IP="127.0.0.1",
+                                 SCHEDULER_PORT=str(sport)))
+        time.sleep(0.4)
+        try:
+            env = base_env(tmp, LD_PRELOAD=kb.LIB_PATH, GEMHOOK_SCHEDULER_IP="127.0.0.1", POD_MANAGER_PORT=pport,
+                           POD_NAME="bench/c0")
+            check_memsweep(run_storm(env, "--mode", "memsweep"), GIB8)
+        finally:
+            pmgr.kill()
+            schd.kill()
+            pmgr.wait()
+            schd.wait()
+
+
+# ------------------------------------------------------------------------------------------ co-resident clients
+def test_two_clients_share_one_token_through_the_pool():
+    with tempfile.TemporaryDirectory() as tmp:
+        quota = "2\nbench/c0 0.5 1.0 %d\nbench/c1 0.5 1.0 %d\n" % (GIB8, GIB8)
+        procs = []
+        for i in range(2):
+            env = hooked_env(tmp, pod="bench/c%d" % i, quota=quota, GEMHOOK_BASE_QUOTA_MS=30, GEMHOOK_MIN_QUOTA_MS=5,
+                             STUB_REPORT=os.path.join(tmp, "stub%d.json" % i))
+            procs.append(sp.Popen([kb.STORM_PATH, "--mode", "storm", "--steps", "4", "--warmup", "1", "--step-launches", "20000",
+                                   "--sync-every", "500", "--client-id", str(i), "--nclients", "2", "--barrier-dir", tmp,
+                                   "--out", os.path.join(tmp, "out%d.json" % i)], env=env, stderr=sp.PIPE))
+        for p in procs:
+            _, err = p.communicate(timeout=120)
+            assert p.returncode == 0, err.decode()[-1000:]
+        st = stats_files(tmp)
+        assert len(st) == 2 and all(s["launches"] == 100000 for s in st)
+        assert all(s["token_requests"] >= 3 for s in st)       # both had to renew: the token really moved
+        assert sum(s["token_wait_ms"] for s in st) > 10.0      # somebody waited while the other held it
+        L = kb.lib()
+        p = L.gemhook_pool_open(os.path.join(tmp, "pool").encode(), 0, 0, 0, 0, 0)
+        assert p and L.gemhook_pool_nslots(p) == 2
+        acc = [L.gemhook_pool_accumulated_ms(p, k) for k in range(2)]
+        assert all(a > 0 for a in acc)
+        L.gemhook_pool_close(p)
