@@ -1,0 +1,2 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+python -m pytest tests -x -q -m gpu -s 2>&1 | tail -25

@@ -1,0 +1,163 @@
+"""GPU: the live hook on a real B200 -- device accounting vs host sum, gpu_mem cap with real allocations,
+burst-edge token renewals, and accumulated GPU-ms against the reference stack's ledger (+-1 %)."""
+import glob
+import json
+import os
+import signal
+import subprocess as sp
+import tempfile
+import time
+
+import pytest
+
+import kubeshare_b200 as kb
+import orc
+import wireproto as wp
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(kb.ROOT, "oracle", "_ref")
+GIB8 = 8589934592
+
+
+def env_pool(tmp, pod="bench/c0", quota=None, **kw):
+    quota = quota or "1\nbench/c0 1.0 1.0 %d\n" % GIB8
+    with open(os.path.join(tmp, "quota.txt"), "w") as f:
+        f.write(quota)
+    env = {k: v for k, v in os.environ.items() if not k.startswith("GEMHOOK_") and k != "LD_PRELOAD"}
+    env.update(LD_PRELOAD=kb.LIB_PATH, GEMHOOK_POOL=os.path.join(tmp, "pool"), GEMHOOK_QUOTA_FILE=os.path.join(tmp, "quota.txt"),
+               POD_NAME=pod, GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"))
+    env.update({k: str(v) for k, v in kw.items()})
+    return env
+
+
+def storm(env, *args, timeout=300):
+    p = sp.run([kb.STORM_PATH, *map(str, args)], env=env, stdout=sp.PIPE, stderr=sp.PIPE, timeout=timeout)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    return json.loads(p.stdout)
+
+
+def stats(tmp):
+    return [json.load(open(f)) for f in sorted(glob.glob(os.path.join(tmp, "stats.*.json")))]
+
+
+@pytest.mark.parametrize("seg", [0, 256])
+def test_device_reduced_sm_time_equals_host_sum(seg):
+    with tempfile.TemporaryDirectory() as tmp:
+        res = storm(env_pool(tmp, GEMHOOK_SEG_LAUNCHES=seg, GEMHOOK_FLUSH_RECORDS=16), "--mode", "storm", "--steps", 4,
+                    "--warmup", 1, "--step-launches", 16384, "--sync-every", 1024)
+        st = stats(tmp)[0]
+        assert st["launches"] == 5 * 16384
+        assert st["segments"] >= (80 if seg == 0 else 300)
+        assert st["acct_kernels"] >= 2
+        assert st["gpu_ns"] == st["gpu_ns_host"] > 0          # sm_100a reduction == host-side sum, bit-exact
+        # the bursts cover the storm: SM-time within the wall time, and most of it
+        assert 0.5 * res["event_ms"] < st["gpu_ns"] / 1e6 * 4 / 5 < 1.02 * res["event_ms"]
+
+
+def test_config4_real_allocations_bit_exact_oom_point():
+    O = orc.load()
+    with tempfile.TemporaryDirectory() as tmp:
+        res = storm(env_pool(tmp), "--mode", "memsweep")
+    limit, used, first_fail = GIB8, 0, -1
+    for row in res["sweep1"]:
+        ok = O.orc_mem_prehook_allows(row["bytes"], used, limit)
+        assert row["rc"] == (0 if ok else 2), row
+        used += row["bytes"] if ok else 0
+        if not ok and first_fail < 0:
+            first_fail = row["i"]
+        assert (row["free"], row["total"]) == (limit - used, limit)
+    assert res["first_fail"] == first_fail == 8
+    used = 0
+    for sz, rc, free in res["sweep2"]:
+        ok = O.orc_mem_prehook_allows(sz, used, limit)
+        assert rc == (0 if ok else 2)
+        used += sz if ok else 0
+        assert free == limit - used
+    assert res["free_end"] == limit
+
+
+def test_config3_bursty_tokens_renew_only_at_burst_edges():
+    with tempfile.TemporaryDirectory() as tmp:
+        quota = "4\n" + "".join("bench/c%d 0.25 1.0 %d\n" % (i, GIB8) for i in range(4))
+        procs = []
+        for i in range(4):
+            env = env_pool(tmp, pod="bench/c%d" % i, quota=quota)
+            procs.append(sp.Popen([kb.STORM_PATH, "--mode", "bursty", "--rounds", "150", "--client-id", str(i), "--nclients", "4",
+                                   "--barrier-dir", tmp, "--out", os.path.join(tmp, "out%d.json" % i)], env=env, stderr=sp.PIPE))
+        for p in procs:
+            _, err = p.communicate(timeout=600)
+            assert p.returncode == 0, err.decode()[-1000:]
+        st = stats(tmp)
+        outs = [json.load(open(os.path.join(tmp, "out%d.json" % i))) for i in range(4)]
+        assert len(st) == 4
+        for s in st:
+            o = [x for x in outs if x["launches"] == s["launches"]]
+            assert o, "every launch intercepted"
+            assert s["slow_path"] <= 150 + s["token_requests"] + 2   # one slow path per burst (+ tracker-forced edges)
+            assert s["token_requests"] <= s["slow_path"] + 1          # renewals happen only on the slow path
+            assert s["gpu_ns"] == s["gpu_ns_host"] > 0
+        # 4 clients x ~150 bursts x ~2000 launches x 5 us: everybody got GPU time, nobody starved
+        busy = [s["gpu_ns"] for s in st]
+        assert min(busy) > 0.3 * max(busy)
+
+
+def _ledger_total(path, pod):
+    led = json.load(open(path))
+    return sum(e["end"] - e["start"] for e in led if e["container"] == pod) * 1e3, len(led)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "gem-schd-dbg")), reason="oracle/_ref not built")
+def test_accumulated_gpu_ms_within_1pct_of_reference_ledger():
+    """Same storm through (a) the reference hook and (b) our hook, each against fresh UNMODIFIED gem-pmgr +
+    gem-schd(_DEBUG); gem-schd's own ledger dump (scheduler.cpp:693-714) is the judge: sum(end-start)."""
+    try:
+        os.makedirs("/kubeshare/library", exist_ok=True)
+        os.makedirs("/kubeshare/log", exist_ok=True)
+        with open("/kubeshare/library/schedulerIP.txt", "w") as f:
+            f.write("127.0.0.1\n")
+    except OSError:
+        pytest.skip("cannot create /kubeshare/library (the reference hook hard-codes it)")
+    totals = {}
+    for which in ("reference", "ours"):
+        with tempfile.TemporaryDirectory() as tmp:
+            with open(os.path.join(tmp, "cfg.txt"), "w") as f:
+                f.write("1\nbench/c0 1.0 1.0 %d\n" % GIB8)
+            sport, pport = wp.free_port(), wp.free_port()
+            schd = sp.Popen([os.path.join(REF, "gem-schd-dbg"), "-p", tmp, "-f", "cfg.txt", "-P", str(sport), "-q", "300", "-m",
+                             "20", "-w", "10000", "-v", "1"], cwd=tmp, stdout=sp.DEVNULL, stderr=sp.DEVNULL)
+            time.sleep(0.5)
+            pmgr = sp.Popen([os.path.join(REF, "gem-pmgr")], stdout=sp.DEVNULL, stderr=sp.DEVNULL,
+                            env=dict(os.environ, POD_NAME="bench/c0", POD_MANAGER_PORT=str(pport), SCHEDULER_IP="127.0.0.1",
+                                     SCHEDULER_PORT=str(sport)))
+            time.sleep(0.5)
+            try:
+                env = {k: v for k, v in os.environ.items() if not k.startswith("GEMHOOK_") and k != "LD_PRELOAD"}
+                env.update(POD_NAME="bench/c0", POD_MANAGER_PORT=str(pport))
+                if which == "ours":
+                    env.update(LD_PRELOAD=kb.LIB_PATH, GEMHOOK_SCHEDULER_IP="127.0.0.1",
+                               GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"))
+                else:
+                    env.update(LD_PRELOAD=os.path.join(REF, "libgemhook_ref.so.1"))
+                res = storm(env, "--mode", "storm", "--steps", 12, "--warmup", 2, "--step-launches", 65536)
+                time.sleep(0.2)
+                schd.send_signal(signal.SIGINT)
+                schd.wait(timeout=20)
+                dumps = glob.glob(os.path.join(tmp, "*.json"))
+                dumps = [d for d in dumps if os.path.basename(d)[0].isdigit()]
+                assert dumps, "gem-schd did not dump its ledger"
+                total_ms, n = _ledger_total(dumps[0], "bench/c0")
+                extra = stats(tmp)[0] if which == "ours" else {}
+                totals[which] = {"ledger_ms": total_ms, "tokens": n, "wall_ms": res["wall_s"] * 1e3, "stats": extra}
+            finally:
+                pmgr.kill()
+                schd.kill()
+                pmgr.wait()
+                schd.wait()
+    ref, ours = totals["reference"], totals["ours"]
+    print("ledger totals:", json.dumps(totals))
+    # identical launch trace, identical policy, identical daemons: the ledgers agree within 1 %
+    assert abs(ours["ledger_ms"] - ref["ledger_ms"]) <= 0.01 * ref["ledger_ms"], totals
+    # and our own per-token view of the same quantity matches what gem-schd recorded for us (within 1 %)
+    # (closed tokens as the hook saw them + the token still held at exit, which the ledger carries at full quota)
+    mine = ours["stats"]["accumulated_token_ms"] + ours["stats"]["quota_ms"]
+    assert abs(mine - ours["ledger_ms"]) <= 0.01 * ours["ledger_ms"], (mine, ours)
