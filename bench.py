@@ -429,9 +429,16 @@ def main():
         peak = (peaks or {}).get("hbm_gbs", 6650.0)
         if roof:
             big = roof["ring_2p26"]
+            traffic = None
+            try:  # dram read+write bytes per launch of the same kernel/size from the committed ncu --set full capture
+                tj = json.load(open(os.path.join(ROOT, "profiles", "acct_reduce_traffic.json")))
+                if tj.get("records") == big["records"]:
+                    traffic = tj["traffic_bytes_per_launch"]
+            except (OSError, ValueError, KeyError):
+                pass
             line["roofline"] = {"bound": "hbm", "kernel": "gemhook_acct_reduce", "achieved": big["gbps"], "peak": peak,
                                 "unit": "GB/s", "frac": big["gbps"] / peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
-                                "traffic": None, "records": big["records"], "avg_ms": big["avg_ms"], "grid": big["grid"],
+                                "traffic": traffic, "algorithmic_bytes": big["bytes"], "records": big["records"], "avg_ms": big["avg_ms"], "grid": big["grid"],
                                 "ring_2p20": roof["ring_2p20"], "cpu_oracle": roof["cpu_oracle"]}
         if cpu_ref:
             line["cpu_baseline"] = {"value": cpu_ref["launches_per_s_host"], "unit": "launches/s", "kind": "reference",
