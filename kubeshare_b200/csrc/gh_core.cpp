@@ -138,6 +138,7 @@ void gh_config_load(void) {
   c.extra_hooks = (int)env_i("GEMHOOK_EXTRA_HOOKS", 0);
   c.exit_on_failure = (int)env_i("GEMHOOK_EXIT_ON_FAILURE", 1);
   c.seg_launches = (uint32_t)env_i("GEMHOOK_SEG_LAUNCHES", 0);  // 0 = burst edges only
+  c.seg_min_us = (uint32_t)env_i("GEMHOOK_SEG_MIN_US", 4000);
   c.flush_records = (uint32_t)env_i("GEMHOOK_FLUSH_RECORDS", 64);
   c.base_quota_ms = env_f("GEMHOOK_BASE_QUOTA_MS", 300.0);  // reference launcher.py:77-80
   c.min_quota_ms = env_f("GEMHOOK_MIN_QUOTA_MS", 20.0);

@@ -71,7 +71,14 @@ struct gh_live {
   struct Pending {
     int ev_begin, ev_end;
     uint32_t launches;
+    uint64_t idle_ns;  // host-measured idle gaps inside a merged segment, subtracted from the event span
   } pending[SEG_EVENTS];
+  // segment merging: a segment is closed at a sync only once it is at least seg_min_ns old, so sync-heavy
+  // applications do not pay two event records per tiny burst; the idle gaps it then spans are measured on
+  // the host clock (sync return -> next launch) and subtracted
+  int64_t seg_begin_host_ns = 0, seg_sync_return_ns = 0;
+  uint64_t seg_idle_ns = 0;
+  bool seg_spans_sync = false;
   int npending = 0;
   bool seg_end_recorded = false;
 
@@ -126,6 +133,7 @@ static double token_from_scheduler(gh_live* L, double overuse_ms, double next_bu
 // ---- overuse tracker ----------------------------------------------------------------------------------
 static void host_sync_locked(gh_live* L, int64_t now);
 static void resolve_pending_locked(gh_live* L, bool may_block, int skip_last = 0);
+static void sync_pre(bool force);
 
 static void* tracker_main(void* arg) {
   gh_live* L = (gh_live*)arg;
@@ -148,7 +156,7 @@ static void* tracker_main(void* arg) {
     // streams (hook.cpp:449-453, 482-485); the events are reused, not leaked per token.
     float elapsed_ms = 0.f;
     if (!gh_cfg.dry_run) {
-      gh_host_sync_pre();  // close the running accounting segment on its own stream first
+      sync_pre(true);  // close the running accounting segment on its own stream first
       GH_CALL(cuEventRecord, L->ev_drain, (CUstream)0);
       GH_CALL(cuEventSynchronize, L->ev_drain);
       GH_CALL(cuEventElapsedTime, &elapsed_ms, L->ev_token, L->ev_drain);
@@ -206,11 +214,21 @@ static void seg_begin_locked(gh_live* L, CUstream stream) {
   if (gh_cfg.dry_run || !L->cuda_ready) return;
   // events are a ring: never re-record one that an unresolved segment still refers to
   if (L->npending > SEG_EVENTS / 2) resolve_pending_locked(L, true);
+  int64_t now = gh_now_ns();
+  if (L->seg_open && L->seg_spans_sync) {  // the running segment continues across the sync we just passed
+    if (L->seg_sync_return_ns && now > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(now - L->seg_sync_return_ns);
+    L->seg_spans_sync = false;
+    L->seg_stream = stream;
+    return;
+  }
   L->seg_head = (L->seg_head + 1) % SEG_EVENTS;
   if (GH_CALL(cuEventRecord, L->seg_ev[L->seg_head], stream) != CUDA_SUCCESS) return;
   L->seg_open = true;
   L->seg_end_recorded = false;
+  L->seg_spans_sync = false;
   L->seg_stream = stream;
+  L->seg_begin_host_ns = now;
+  L->seg_idle_ns = 0;
   L->seg_first_launch = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
 }
 
@@ -223,10 +241,12 @@ void gh_segment_tick(CUstream stream) {
     int nxt = (L->seg_head + 1) % SEG_EVENTS;
     if (GH_CALL(cuEventRecord, L->seg_ev[nxt], stream) == CUDA_SUCCESS) {
       uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
-      L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch)};
+      L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch), L->seg_idle_ns};
       L->seg_head = nxt;
       L->seg_first_launch = n;
       L->seg_stream = stream;
+      L->seg_idle_ns = 0;
+      L->seg_begin_host_ns = gh_now_ns();
     }
   }
   pthread_mutex_unlock(&L->mu);
@@ -234,17 +254,25 @@ void gh_segment_tick(CUstream stream) {
 
 // before a synchronising driver call: mark the end of the running segment on its stream, so that the
 // event carries the completion time of the burst's last kernel rather than the host's return time
-void gh_host_sync_pre(void) {
+static void sync_pre(bool force) {
   gh_live* L = g_live;
   if (!L || !L->cuda_ready || gh_cfg.dry_run) return;
   if (!L->seg_open && L->npending == 0 && L->stage_n < gh_cfg.flush_records) return;
   pthread_mutex_lock(&L->mu);
   int fresh = 0;
-  if (L->seg_open && !L->seg_end_recorded && L->npending < SEG_EVENTS - 2) {
+  bool old_enough = force || (gh_now_ns() - L->seg_begin_host_ns >= (int64_t)gh_cfg.seg_min_us * 1000);
+  if (L->seg_open && !L->seg_end_recorded && !old_enough) {
+    L->seg_spans_sync = true;  // keep it open across this sync
+  } else if (L->seg_open && !L->seg_end_recorded && L->npending < SEG_EVENTS - 2) {
+    if (L->seg_spans_sync && L->seg_sync_return_ns) {  // forced close while idle after a merged sync
+      int64_t t = gh_now_ns();
+      if (t > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(t - L->seg_sync_return_ns);
+      L->seg_spans_sync = false;
+    }
     int nxt = (L->seg_head + 1) % SEG_EVENTS;
     if (GH_CALL(cuEventRecord, L->seg_ev[nxt], L->seg_stream) == CUDA_SUCCESS) {
       uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
-      L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch)};
+      L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch), L->seg_idle_ns};
       L->seg_head = nxt;
       L->seg_end_recorded = true;
       fresh = 1;
@@ -259,6 +287,7 @@ void gh_host_sync_pre(void) {
   flush_stage_locked(L, false);
   pthread_mutex_unlock(&L->mu);
 }
+void gh_host_sync_pre(void) { sync_pre(false); }
 
 // all pending events are complete after a host sync: turn them into records
 static void resolve_pending_locked(gh_live* L, bool may_block, int skip_last) {
@@ -277,7 +306,7 @@ static void resolve_pending_locked(gh_live* L, bool may_block, int skip_last) {
       r = GH_CALL(cuEventElapsedTime, &ms, L->seg_ev[p.ev_begin], L->seg_ev[p.ev_end]);
     }
     if (r == CUDA_SUCCESS) {
-      double ns = (double)ms * 1e6;
+      double ns = (double)ms * 1e6 - (double)p.idle_ns;
       stage_record(L, p.launches, ns > 0 ? (uint64_t)(ns + 0.5) : 0);
     } else if (r == CUDA_ERROR_NOT_READY) {
       L->pending[kept++] = p;  // a sync on another stream only: try again later
@@ -289,7 +318,8 @@ static void resolve_pending_locked(gh_live* L, bool may_block, int skip_last) {
 static void host_sync_locked(gh_live* L, int64_t now) {
   gemhook_gate_host_sync(L->gate, now);
   gh_gate_open = 0;
-  L->seg_open = false;
+  if (L->seg_open && L->seg_spans_sync && !L->seg_end_recorded) L->seg_sync_return_ns = now;  // merged: stays open
+  else L->seg_open = false;
 }
 
 void gh_host_sync_post(void) {
@@ -467,8 +497,9 @@ GH_EXPORT int gemhook_flush(void) {
   pthread_mutex_lock(&L->mu);
   if (L->seg_open && !L->seg_end_recorded) {
     pthread_mutex_unlock(&L->mu);
-    gh_host_sync_pre();
+    sync_pre(true);
     pthread_mutex_lock(&L->mu);
+    L->seg_open = false;
   }
   resolve_pending_locked(L, true);
   flush_stage_locked(L, true);

@@ -100,6 +100,7 @@ struct gh_config {
   int extra_hooks;
   int exit_on_failure;    // reference behaviour: exit() when the scheduler is unreachable
   uint32_t seg_launches;  // K
+  uint32_t seg_min_us;    // a segment is closed at a sync only when it is at least this old
   uint32_t flush_records;
   double base_quota_ms, min_quota_ms, window_ms;
   int disabled;

@@ -47,7 +47,7 @@ def test_device_reduced_sm_time_equals_host_sum(seg):
                     "--warmup", 1, "--step-launches", 16384, "--sync-every", 1024)
         st = stats(tmp)[0]
         assert st["launches"] == 5 * 16384
-        assert st["segments"] >= (80 if seg == 0 else 300)
+        assert st["segments"] >= (20 if seg == 0 else 300)   # bursts younger than GEMHOOK_SEG_MIN_US merge
         assert st["acct_kernels"] >= 2
         assert st["gpu_ns"] == st["gpu_ns_host"] > 0          # sm_100a reduction == host-side sum, bit-exact
         # the bursts cover the storm: SM-time within the wall time, and most of it
