@@ -157,6 +157,18 @@ void gemhook_pool_release(gemhook_pool *, int slot);
 /* declare the outstanding token timed out (scheduler.cpp:507-510) without touching the ledger. */
 void gemhook_pool_expire_token(gemhook_pool *);
 
+/* process attachment: liveness is an OFD byte-range lock on the pool file, so bytes (and a held token) of a
+ * process that died without cleaning up are reclaimed by gemhook_pool_reap() -- the reference does this on
+ * socket close (pod-manager.cpp:533-545). mem_reserve/release through an attached handle are tracked per process. */
+int gemhook_pool_attach(gemhook_pool *, int slot); /* attachment index or -1 */
+void gemhook_pool_detach(gemhook_pool *);
+int gemhook_pool_reap(gemhook_pool *);              /* number of dead attachments reclaimed */
+/* pod-level token shared by the processes of one pod (gem-pmgr's hook_kernel_launch, pod-manager.cpp:316-473):
+ * 1 = must be forwarded to the scheduler with (fwd_overuse, fwd_burst); 0 = answered locally, *remain_ms. */
+int gemhook_pool_pod_launch(gemhook_pool *, int slot, int64_t now_us, double overuse_ms, double burst_ms,
+                            double *fwd_overuse_ms, double *fwd_burst_ms, double *remain_ms);
+double gemhook_pool_pod_granted(gemhook_pool *, int slot, int64_t now_us, double quota_ms);
+
 /* gpu_mem cap on the pool slot (hook.cpp:590-617, pod-manager.cpp:295-313): uint64, requested bytes. */
 int gemhook_pool_mem_reserve(gemhook_pool *, int slot, uint64_t bytes);   /* 1 ok, 0 over the cap */
 void gemhook_pool_mem_release(gemhook_pool *, int slot, uint64_t bytes);

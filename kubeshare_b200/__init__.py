@@ -86,6 +86,10 @@ def lib():
         "gemhook_pool_acquire": (d, [vp, C.c_int, d, d]),
         "gemhook_pool_release": (None, [vp, C.c_int]),
         "gemhook_pool_expire_token": (None, [vp]),
+        "gemhook_pool_attach": (C.c_int, [vp, C.c_int]), "gemhook_pool_detach": (None, [vp]),
+        "gemhook_pool_reap": (C.c_int, [vp]),
+        "gemhook_pool_pod_launch": (C.c_int, [vp, C.c_int, i64, d, d, pd, pd, pd]),
+        "gemhook_pool_pod_granted": (d, [vp, C.c_int, i64, d]),
         "gemhook_pool_mem_reserve": (C.c_int, [vp, C.c_int, u64]),
         "gemhook_pool_mem_release": (None, [vp, C.c_int, u64]),
         "gemhook_pool_mem_info": (None, [vp, C.c_int, C.POINTER(u64), C.POINTER(u64)]),

@@ -371,6 +371,10 @@ static void live_init(void) {
     } else {
       read_quota_file_into_pool(L);
       L->slot = gemhook_pool_find(L->pool, gh_cfg.pod_name);
+      if (L->slot >= 0) {
+        gemhook_pool_reap(L->pool);  // leftovers of clients that died without cleaning up
+        gemhook_pool_attach(L->pool, L->slot);
+      }
       if (L->slot < 0) {
         char msg[256];
         snprintf(msg, sizeof(msg), "pod \"%s\" is not in the quota file / credit pool", gh_cfg.pod_name);
@@ -545,7 +549,10 @@ void gh_register_exit_hook(void);
 static void write_stats_file(void) {
   const char* pat = getenv("GEMHOOK_STATS_FILE");
   gh_live* L = g_live;
-  if (L && L->enabled && L->pool) gemhook_pool_release(L->pool, L->slot);  // do not make peers wait for a timeout
+  if (L && L->enabled && L->pool) {
+    gemhook_pool_release(L->pool, L->slot);  // do not make peers wait for a timeout
+    gemhook_pool_detach(L->pool);            // bytes this process never freed go back to the pod's budget
+  }
   if (!pat || !*pat || !L) return;
   gemhook_flush();
   gemhook_stats s;

@@ -17,8 +17,12 @@
 //
 // The region is plain memory: it can be cuMemHostRegister'ed (gh_hook.cpp does) so the device sees
 // the same counters ("shared-pinned").
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <errno.h>
 #include <fcntl.h>
+#include <stddef.h>
 #include <linux/futex.h>
 #include <sched.h>
 #include <math.h>
@@ -39,7 +43,8 @@
 namespace {
 
 const uint64_t POOL_MAGIC = 0x314c4f4f504d4547ULL;  // "GEMPOOL1"
-const uint32_t POOL_VERSION = 1;
+const uint32_t POOL_VERSION = 2;
+const uint32_t MAX_ATTACH = 256;
 const uint32_t LEDGER_CAP = 8192;
 enum { ST_IDLE = 0, ST_WAITING = 1, ST_GRANTED = 2 };
 
@@ -66,7 +71,11 @@ struct alignas(64) Slot {
   // line 3: counters other parties read
   std::atomic<uint64_t> mem_used;
   std::atomic<uint64_t> gpu_ns, launches;
-  uint64_t _pad3[5];
+  // pod-level token shared by the processes of one pod (gem-pmgr's role, pod-manager.cpp:97-101)
+  double pod_quota;       // pod_quota
+  int64_t pod_token_us;   // quota_updated_tp, microseconds since pool start
+  double pod_overuse;     // pod_overuse_ms
+  uint64_t _pad3[2];
 };
 static_assert(sizeof(Slot) == 256, "slot layout");
 
@@ -97,10 +106,24 @@ struct alignas(64) Header {
   uint32_t ledger_dropped;
 };
 
+// one entry per attached process; byte 0 of each entry is covered by an OFD lock held by the owner for its
+// lifetime -- the kernel drops it when the process dies, in any container, which is how a dead client's
+// bytes are found and reclaimed (the reference reclaims on socket close, pod-manager.cpp:533-545)
+struct Attach {
+  std::atomic<uint32_t> in_use;
+  int32_t slot;
+  std::atomic<uint64_t> bytes;
+  double burst;  // client_burst_map entry (pod-manager.cpp:98)
+  uint32_t pid;
+  uint32_t _pad;
+};
+static_assert(sizeof(Attach) == 32, "attach layout");
+
 struct Region {
   Header h;
   Slot slots[GEMHOOK_MAX_SLOTS];
   Span ledger[LEDGER_CAP];
+  Attach attach[MAX_ATTACH];
 };
 
 long futex(std::atomic<uint32_t>* addr, int op, uint32_t val, const struct timespec* ts) {
@@ -129,6 +152,29 @@ struct gemhook_pool {
   Region* r = nullptr;
   int fd = -1;
   bool anonymous = false;
+  int attach_idx = -1;  // this handle's attachment (set by gemhook_pool_attach)
+
+  int attach_lock(int idx, bool take) {
+    if (fd < 0) return 0;
+    struct flock fl;
+    memset(&fl, 0, sizeof(fl));
+    fl.l_type = take ? F_WRLCK : F_UNLCK;
+    fl.l_whence = SEEK_SET;
+    fl.l_start = (off_t)(offsetof(Region, attach) + (size_t)idx * sizeof(Attach));
+    fl.l_len = 1;
+    return fcntl(fd, F_OFD_SETLK, &fl);
+  }
+  bool attach_owner_alive(int idx) {
+    if (fd < 0) return true;
+    struct flock fl;
+    memset(&fl, 0, sizeof(fl));
+    fl.l_type = F_WRLCK;
+    fl.l_whence = SEEK_SET;
+    fl.l_start = (off_t)(offsetof(Region, attach) + (size_t)idx * sizeof(Attach));
+    fl.l_len = 1;
+    if (fcntl(fd, F_OFD_GETLK, &fl) != 0) return true;  // cannot tell: assume alive
+    return fl.l_type != F_UNLCK;
+  }
 
   void lock() {
     uint32_t me = (uint32_t)getpid();
@@ -282,7 +328,8 @@ struct gemhook_pool {
     return 1;
   }
 
-  double now_ms() const { return (double)((gh_now_ns() - r->h.start_ns) / 1000) / 1e3; }  // scheduler.cpp:107-109
+  int64_t now_us() const { return (gh_now_ns() - r->h.start_ns) / 1000; }
+  double now_ms() const { return (double)now_us() / 1e3; }  // scheduler.cpp:107-109
 };
 
 GH_EXPORT gemhook_pool* gemhook_pool_open(const char* path, int create, double base_quota_ms, double min_quota_ms,
@@ -473,12 +520,22 @@ GH_EXPORT double gemhook_pool_accumulated_ms(const gemhook_pool* p, int slot) {
   return s.grants ? s.closed_ms + (s.last_end - s.last_start) : 0.0;
 }
 
+static int pod_launch_locked(gemhook_pool* p, int slot, int attach_idx, int64_t now_us, double overuse, double burst,
+                             double* fwd_overuse, double* fwd_burst, double* remain);
+static double pod_granted_locked(gemhook_pool* p, int slot, int64_t now_us, double quota);
+
 // Live acquisition: post the request, then arbitrate/wait until OUR slot is granted.
 GH_EXPORT double gemhook_pool_acquire(gemhook_pool* p, int slot, double overuse_ms, double burst_ms) {
   Slot& me = p->r->slots[slot];
   p->lock();
-  request_locked(p, slot, p->now_ms(), overuse_ms, burst_ms);
+  double fo = overuse_ms, fb = burst_ms, remain = 0.0;
+  if (!pod_launch_locked(p, slot, p->attach_idx, p->now_us(), overuse_ms, burst_ms, &fo, &fb, &remain)) {
+    p->unlock();
+    return remain;  // the pod's token still covers this burst (pod-manager.cpp:472)
+  }
+  request_locked(p, slot, p->now_ms(), fo, fb);
   p->unlock();
+  int idle_rounds = 0;
   for (;;) {
     int who = -1;
     double q = 0, sleep_ms = 0;
@@ -489,8 +546,12 @@ GH_EXPORT double gemhook_pool_acquire(gemhook_pool* p, int slot, double overuse_
     if (me.state.load(std::memory_order_acquire) == ST_GRANTED) {
       double got = me.granted_quota;
       me.state.store(ST_IDLE, std::memory_order_release);
+      p->lock();
+      got = pod_granted_locked(p, slot, p->now_us(), got);
+      p->unlock();
       return got;
     }
+    if (++idle_rounds % 8 == 0) gemhook_pool_reap(p);  // a dead holder must not stall everybody until its deadline
     // someone else holds the token, or everyone is throttled: sleep on our own slot word until the hint
     // expires or a granter wakes us.  Short waits spin (no context switch on a quick hand-over).
     double wait_ms = (rc == 0 || rc == -2) ? sleep_ms : 0.2;
@@ -504,6 +565,107 @@ GH_EXPORT double gemhook_pool_acquire(gemhook_pool* p, int slot, double overuse_
     ts.tv_nsec = (long)((wait_ms - ts.tv_sec * 1e3) * 1e6);
     futex(&me.state, FUTEX_WAIT, ST_WAITING, &ts);
   }
+}
+
+// ---- attachments ------------------------------------------------------------------------------------------
+GH_EXPORT int gemhook_pool_attach(gemhook_pool* p, int slot) {
+  if (!p || slot < 0) return -1;
+  for (uint32_t i = 0; i < MAX_ATTACH; i++) {
+    uint32_t exp = 0;
+    if (p->r->attach[i].in_use.compare_exchange_strong(exp, 1u)) {
+      Attach& a = p->r->attach[i];
+      a.slot = slot;
+      a.bytes.store(0);
+      a.burst = 0.0;
+      a.pid = (uint32_t)getpid();
+      p->attach_lock((int)i, true);
+      p->attach_idx = (int)i;
+      return (int)i;
+    }
+  }
+  gh_set_error("credit pool: more than %u attached processes", MAX_ATTACH);
+  return -1;
+}
+
+GH_EXPORT void gemhook_pool_detach(gemhook_pool* p) {
+  if (!p || p->attach_idx < 0) return;
+  Attach& a = p->r->attach[p->attach_idx];
+  uint64_t left = a.bytes.exchange(0);
+  if (left) p->r->slots[a.slot].mem_used.fetch_sub(left, std::memory_order_acq_rel);  // exit without freeing
+  p->attach_lock(p->attach_idx, false);
+  a.in_use.store(0, std::memory_order_release);
+  p->attach_idx = -1;
+}
+
+// reclaim what dead processes left behind: their bytes, and the token if one of them held it
+GH_EXPORT int gemhook_pool_reap(gemhook_pool* p) {
+  if (!p) return 0;
+  int reaped = 0;
+  for (uint32_t i = 0; i < MAX_ATTACH; i++) {
+    Attach& a = p->r->attach[i];
+    if (!a.in_use.load(std::memory_order_acquire) || (int)i == p->attach_idx) continue;
+    if (p->attach_owner_alive((int)i)) continue;
+    p->lock();
+    if (a.in_use.load() && !p->attach_owner_alive((int)i)) {
+      uint64_t left = a.bytes.exchange(0);
+      if (left) p->r->slots[a.slot].mem_used.fetch_sub(left, std::memory_order_acq_rel);
+      bool others = false;
+      for (uint32_t j = 0; j < MAX_ATTACH; j++)
+        if (j != i && p->r->attach[j].in_use.load() && p->r->attach[j].slot == a.slot) others = true;
+      if (!others) {
+        if (p->r->h.holder == a.slot) p->r->h.holder = -1;
+        uint32_t st = p->r->slots[a.slot].state.load();
+        if (st != ST_IDLE) p->r->slots[a.slot].state.store(ST_IDLE);
+      }
+      a.in_use.store(0, std::memory_order_release);
+      reaped++;
+    }
+    p->unlock();
+  }
+  return reaped;
+}
+
+// ---- pod-level token (gem-pmgr hook_kernel_launch, pod-manager.cpp:316-473) -----------------------------------
+// Processes of one pod share the pod's token: a request is answered locally with the REMAINING pod quota unless
+// `elapsed + burst > pod_quota`, in which case it is forwarded to the scheduler with the pod's maximum overuse and
+// the maximum burst over its processes.  Returns 1 = forward (fwd_* filled), 0 = answered (*remain_ms).
+static int pod_launch_locked(gemhook_pool* p, int slot, int attach_idx, int64_t now_us, double overuse, double burst,
+                             double* fwd_overuse, double* fwd_burst, double* remain) {
+  Slot& s = p->r->slots[slot];
+  s.pod_overuse = std::max(overuse, s.pod_overuse);
+  if (attach_idx >= 0) p->r->attach[attach_idx].burst = burst;
+  double elapsed = (double)(now_us - s.pod_token_us) / 1e3;
+  if (elapsed + burst > s.pod_quota) {
+    double mx = attach_idx >= 0 ? 0.0 : burst;
+    for (uint32_t i = 0; i < MAX_ATTACH; i++)
+      if (p->r->attach[i].in_use.load(std::memory_order_relaxed) && p->r->attach[i].slot == slot)
+        mx = std::max(p->r->attach[i].burst, mx);
+    if (fwd_overuse) *fwd_overuse = s.pod_overuse;
+    if (fwd_burst) *fwd_burst = mx;
+    return 1;
+  }
+  if (remain) *remain = s.pod_quota - elapsed;
+  return 0;
+}
+static double pod_granted_locked(gemhook_pool* p, int slot, int64_t now_us, double quota) {
+  Slot& s = p->r->slots[slot];
+  s.pod_quota = quota;
+  s.pod_token_us = now_us;
+  s.pod_overuse = 0.0;
+  return s.pod_quota - 0.0;
+}
+GH_EXPORT int gemhook_pool_pod_launch(gemhook_pool* p, int slot, int64_t now_us, double overuse_ms, double burst_ms,
+                                      double* fwd_overuse_ms, double* fwd_burst_ms, double* remain_ms) {
+  p->lock();
+  int rc = pod_launch_locked(p, slot, p->attach_idx, now_us, overuse_ms, burst_ms, fwd_overuse_ms, fwd_burst_ms, remain_ms);
+  p->unlock();
+  return rc;
+}
+GH_EXPORT double gemhook_pool_pod_granted(gemhook_pool* p, int slot, int64_t now_us, double quota_ms) {
+  p->lock();
+  double r = pod_granted_locked(p, slot, now_us, quota_ms);
+  p->unlock();
+  return r;
 }
 
 // A client that is going away (process exit) hands its token back instead of letting the scheduler wait
@@ -550,11 +712,17 @@ GH_EXPORT int gemhook_pool_mem_reserve(gemhook_pool* p, int slot, uint64_t bytes
     // reference pre-hook: remain = limit - used (size_t arithmetic); deny iff bytes > remain
     uint64_t remain = s.mem_limit - used;
     if (bytes > remain) return 0;
-    if (s.mem_used.compare_exchange_weak(used, used + bytes, std::memory_order_acq_rel)) return 1;
+    if (s.mem_used.compare_exchange_weak(used, used + bytes, std::memory_order_acq_rel)) {
+      if (p->attach_idx >= 0 && p->r->attach[p->attach_idx].slot == slot)
+        p->r->attach[p->attach_idx].bytes.fetch_add(bytes, std::memory_order_relaxed);
+      return 1;
+    }
   }
 }
 GH_EXPORT void gemhook_pool_mem_release(gemhook_pool* p, int slot, uint64_t bytes) {
   p->r->slots[slot].mem_used.fetch_sub(bytes, std::memory_order_acq_rel);
+  if (p->attach_idx >= 0 && p->r->attach[p->attach_idx].slot == slot)
+    p->r->attach[p->attach_idx].bytes.fetch_sub(bytes, std::memory_order_relaxed);
 }
 GH_EXPORT void gemhook_pool_mem_info(const gemhook_pool* p, int slot, uint64_t* used, uint64_t* limit) {
   if (used) *used = p->r->slots[slot].mem_used.load(std::memory_order_acquire);

@@ -217,3 +217,106 @@ def test_quota_file_column_order_trap():
             assert L.gemhook_pool_schedule(p, t, C.byref(who), C.byref(q), C.byref(slp)) == 1
         assert q.value == expect_max * 10000.0
         L.gemhook_pool_close(p)
+
+
+def test_pod_level_token_rule_matches_reference_pmgr():
+    """gem-pmgr's forwarding rule (pod-manager.cpp:316-473): golden from the live binary + oracle on random traces."""
+    import random
+
+    g = G["live_pmgr_forward"]
+    L, O = kb.lib(), orc.load()
+    p = L.gemhook_pool_open(None, 1, 300.0, 20.0, 10000.0, 1)
+    L.gemhook_pool_load_config(p, b"1\nns/pod 1.0 1.0 123456789\n", 0)
+    fo, fb, rem = C.c_double(), C.c_double(), C.c_double()
+    now = 0
+    for st in g["steps"]:
+        now += 1
+        fwd = L.gemhook_pool_pod_launch(p, 0, now, st["overuse"], st["burst"], C.byref(fo), C.byref(fb), C.byref(rem))
+        if st["forwarded"] is None:
+            assert fwd == 0 and rem.value <= prev_quota
+        else:
+            assert fwd == 1 and (fo.value, fb.value) == (st["forwarded"]["overuse"], st["forwarded"]["burst"])
+            assert L.gemhook_pool_pod_granted(p, 0, now, st["schd_quota"]) == st["reply_quota"]
+            prev_quota = st["schd_quota"]
+    L.gemhook_pool_close(p)
+
+    # random trace, two processes of one pod (two attachments through two handles on one file)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "pool").encode()
+        a = L.gemhook_pool_open(path, 1, 300.0, 20.0, 10000.0, 1)
+        b = L.gemhook_pool_open(path, 0, 0, 0, 0, 0)
+        L.gemhook_pool_load_config(a, b"1\nns/pod 1.0 1.0 1\n", 0)
+        assert L.gemhook_pool_attach(a, 0) >= 0 and L.gemhook_pool_attach(b, 0) >= 0
+        o = O.orc_pmgr_new(1, 0)
+        O.orc_pmgr_connect(o, 0)
+        O.orc_pmgr_connect(o, 1)
+        rng = random.Random(12)
+        now_us = 0
+        e1, e2, e3 = C.c_double(), C.c_double(), C.c_double()
+        forwards = 0
+        for _ in range(3000):
+            now_us += rng.randrange(1, 400_000)
+            k = rng.randrange(2)
+            over, burst = rng.choice([0.0, 0.0, 2.25]), rng.choice([0.0, 5.0, 80.0, 700.0])
+            r1 = L.gemhook_pool_pod_launch([a, b][k], 0, now_us, over, burst, C.byref(fo), C.byref(fb), C.byref(rem))
+            r2 = O.orc_pmgr_kernel_launch(o, k, now_us * 1000, over, burst, C.byref(e1), C.byref(e2), C.byref(e3))
+            assert r1 == r2
+            if r1:
+                forwards += 1
+                assert (fo.value, fb.value) == (e1.value, e2.value)
+                q = rng.choice([20.0, 300.0, 1234.5])
+                now_us += rng.randrange(10, 5000)
+                assert L.gemhook_pool_pod_granted(a, 0, now_us, q) == O.orc_pmgr_schd_reply(o, now_us * 1000, q)
+            else:
+                assert rem.value == e3.value
+        assert 100 < forwards < 2900
+        L.gemhook_pool_close(b)
+        L.gemhook_pool_close(a)
+        O.orc_pmgr_free(o)
+
+
+def test_dead_process_is_reaped_bytes_and_token():
+    """A client killed with SIGKILL leaves bytes and maybe the token behind; peers reclaim both
+    (reference: reclaim on socket close, pod-manager.cpp:533-545; token by timeout, scheduler.cpp:507-510)."""
+    import signal
+    import subprocess
+    import sys
+    import tempfile
+    import time
+
+    L = kb.lib()
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "pool")
+        p = L.gemhook_pool_open(path.encode(), 1, 300.0, 20.0, 10000.0, 0)
+        L.gemhook_pool_load_config(p, b"2\nA 0.5 1.0 1000\nB 0.5 1.0 1000\n", 0)
+        child = subprocess.Popen([sys.executable, "-c", """
+import sys, time, ctypes as C
+sys.path.insert(0, %r)
+import kubeshare_b200 as kb
+L = kb.lib()
+p = L.gemhook_pool_open(%r.encode(), 0, 0, 0, 0, 0)
+assert L.gemhook_pool_attach(p, 0) >= 0
+assert L.gemhook_pool_mem_reserve(p, 0, 700) == 1
+q = L.gemhook_pool_acquire(p, 0, 0.0, 0.0)
+print('held', q, flush=True)
+time.sleep(60)
+""" % (kb.ROOT, path)], stdout=subprocess.PIPE, text=True)
+        assert child.stdout.readline().startswith("held")
+        u, lim = C.c_uint64(), C.c_uint64()
+        L.gemhook_pool_mem_info(p, 0, C.byref(u), C.byref(lim))
+        assert u.value == 700
+        assert L.gemhook_pool_reap(p) == 0          # alive: nothing to reclaim
+        child.send_signal(signal.SIGKILL)
+        child.wait()
+        time.sleep(0.05)
+        assert L.gemhook_pool_reap(p) == 1
+        L.gemhook_pool_mem_info(p, 0, C.byref(u), C.byref(lim))
+        assert u.value == 0
+        # B can take the token at once although A held a 300 ms quota and never returned it
+        assert L.gemhook_pool_attach(p, 1) >= 0
+        t0 = time.time()
+        assert L.gemhook_pool_acquire(p, 1, 0.0, 0.0) == 300.0
+        assert time.time() - t0 < 0.2
+        L.gemhook_pool_detach(p)
+        L.gemhook_pool_close(p)
