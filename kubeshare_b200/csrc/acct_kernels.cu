@@ -30,7 +30,12 @@
 #include <stdint.h>
 
 #define GEMHOOK_MAX_WARPS_PER_BLOCK 8  /* host picks 8 or 4 warps by shared-memory budget */
-#define GEMHOOK_UNROLL 8
+#ifndef GEMHOOK_UNROLL
+#define GEMHOOK_UNROLL 16              /* independent 16-byte loads in flight per lane (host: gh_acct.cpp TILE_RECORDS) */
+#endif
+#ifndef GEMHOOK_MIN_BLOCKS
+#define GEMHOOK_MIN_BLOCKS 1
+#endif
 
 extern "C" {
 
@@ -70,7 +75,7 @@ __device__ __forceinline__ void bin_add(unsigned long long* ns, unsigned long lo
 
 // dev_totals: [nslots][3] u64 running totals + 1 u64 publish counter (device memory, persistent)
 // ticket:     u32 zero-initialised, self-resetting
-__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, GEMHOOK_MIN_BLOCKS)
 gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigned nslots,
                     unsigned long long* __restrict__ dev_totals, unsigned* __restrict__ ticket,
                     gemhook_totals_page* __restrict__ page) {
@@ -152,7 +157,11 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigne
     if (is_last) *ticket = 0u;  // self-reset for the next launch (stream-ordered)
   }
   __syncthreads();
+#ifdef GEMHOOK_EXP_NO_PUBLISH
+  if (0) {
+#else
   if (is_last && page) {
+#endif
     // dev_totals[nslots*3] is the device-resident publish counter: no read ever crosses PCIe
     __shared__ unsigned long long e_sh;
     __threadfence();

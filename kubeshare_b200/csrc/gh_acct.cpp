@@ -33,7 +33,10 @@ struct totals_page {  // mirrors gemhook_totals_page in acct_kernels.cu
 };
 
 const unsigned BIN_BYTES_PER_SLOT = 32u * 20u;  // GEMHOOK_BIN_BYTES_PER_SLOT
-const unsigned TILE_RECORDS = 32u * 8u;         // records per warp iteration (32 lanes x GEMHOOK_UNROLL)
+#ifndef GEMHOOK_UNROLL
+#define GEMHOOK_UNROLL 16
+#endif
+const unsigned TILE_RECORDS = 32u * GEMHOOK_UNROLL;  // records per warp iteration (32 lanes x GEMHOOK_UNROLL)
 
 const char* cu_err(CUresult r) {
   const char* s = nullptr;

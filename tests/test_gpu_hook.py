@@ -161,3 +161,49 @@ def test_accumulated_gpu_ms_within_1pct_of_reference_ledger():
     # (closed tokens as the hook saw them + the token still held at exit, which the ledger carries at full quota)
     mine = ours["stats"]["accumulated_token_ms"] + ours["stats"]["quota_ms"]
     assert abs(mine - ours["ledger_ms"]) <= 0.01 * ours["ledger_ms"], (mine, ours)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "libgemhook_ref.so.1")), reason="oracle/_ref not built")
+def test_reference_hook_served_by_gem_arbiter_next_to_a_native_client():
+    """Drop-in in the other direction: the UNMODIFIED reference hook speaks TCP to gem-arbiter while a native hook
+    arbitrates in the same pool; both finish, both appear in one ledger."""
+    try:
+        os.makedirs("/kubeshare/library", exist_ok=True)
+        os.makedirs("/kubeshare/log", exist_ok=True)
+        with open("/kubeshare/library/schedulerIP.txt", "w") as f:
+            f.write("127.0.0.1\n")
+    except OSError:
+        pytest.skip("cannot create /kubeshare/library (the reference hook hard-codes it)")
+    arbiter = os.path.join(kb.HERE, "bin", "gem-arbiter")
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "cfg.txt"), "w") as f:
+            f.write("2\nbench/native 0.5 1.0 %d\nbench/legacy 0.5 1.0 %d\n" % (GIB8, GIB8))
+        port = wp.free_port()
+        pool = os.path.join(tmp, "pool")
+        arb = sp.Popen([arbiter, "--pool", pool, "-p", tmp, "-f", "cfg.txt", "-P", str(port), "-q", "300", "-m", "20", "-w",
+                        "10000"], stderr=sp.DEVNULL)
+        time.sleep(0.5)
+        try:
+            base = {k: v for k, v in os.environ.items() if not k.startswith("GEMHOOK_") and k != "LD_PRELOAD"}
+            e_native = dict(base, LD_PRELOAD=kb.LIB_PATH, GEMHOOK_POOL=pool, POD_NAME="bench/native",
+                            GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"))
+            e_legacy = dict(base, LD_PRELOAD=os.path.join(REF, "libgemhook_ref.so.1"), POD_NAME="bench/legacy",
+                            POD_MANAGER_PORT=str(port))
+            args = ["--mode", "storm", "--steps", "6", "--warmup", "1", "--step-launches", "65536", "--nclients", "2",
+                    "--barrier-dir", tmp]
+            procs = [sp.Popen([kb.STORM_PATH, *args, "--client-id", "0", "--out", os.path.join(tmp, "o0.json")], env=e_native, stderr=sp.PIPE),
+                     sp.Popen([kb.STORM_PATH, *args, "--client-id", "1", "--out", os.path.join(tmp, "o1.json")], env=e_legacy, stderr=sp.PIPE)]
+            for p in procs:
+                _, err = p.communicate(timeout=300)
+                assert p.returncode == 0, err.decode()[-1500:]
+            outs = [json.load(open(os.path.join(tmp, "o%d.json" % i))) for i in range(2)]
+            assert all(o["launches"] == 6 * 65536 for o in outs)
+            L = kb.lib()
+            p = L.gemhook_pool_open(pool.encode(), 0, 0, 0, 0, 0)
+            acc = {n: L.gemhook_pool_accumulated_ms(p, L.gemhook_pool_find(p, n.encode())) for n in ("bench/native", "bench/legacy")}
+            L.gemhook_pool_close(p)
+            print("ledger:", acc)
+            assert all(v > 100.0 for v in acc.values()), acc
+        finally:
+            arb.kill()
+            arb.wait()
