@@ -157,6 +157,20 @@ void gemhook_pool_release(gemhook_pool *, int slot);
 /* declare the outstanding token timed out (scheduler.cpp:507-510) without touching the ledger. */
 void gemhook_pool_expire_token(gemhook_pool *);
 
+/* per-client view for exporters (kubeshare-aggregator style scraping) */
+typedef struct gemhook_slot_info {
+  char name[64];
+  double min_frac, max_frac;
+  uint64_t mem_limit, mem_used;
+  uint64_t gpu_ns;        /* SM-time reduced on the device, published by the client's hook */
+  uint64_t launches;
+  uint64_t tokens;        /* tokens granted so far */
+  double quota_ms;        /* current adaptive quota */
+  double accumulated_ms;  /* ledger sum(end-start) */
+  int32_t holds_token, waiting;
+} gemhook_slot_info;
+int gemhook_pool_slot_info(const gemhook_pool *, int slot, gemhook_slot_info *out);
+
 /* process attachment: liveness is an OFD byte-range lock on the pool file, so bytes (and a held token) of a
  * process that died without cleaning up are reclaimed by gemhook_pool_reap() -- the reference does this on
  * socket close (pod-manager.cpp:533-545). mem_reserve/release through an attached handle are tracked per process. */

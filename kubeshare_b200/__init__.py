@@ -32,6 +32,12 @@ class Record(C.Structure):
     _fields_ = [("slot", C.c_uint32), ("launches", C.c_uint32), ("elapsed_ns", C.c_uint64)]
 
 
+class SlotInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("min_frac", C.c_double), ("max_frac", C.c_double), ("mem_limit", C.c_uint64),
+                ("mem_used", C.c_uint64), ("gpu_ns", C.c_uint64), ("launches", C.c_uint64), ("tokens", C.c_uint64),
+                ("quota_ms", C.c_double), ("accumulated_ms", C.c_double), ("holds_token", C.c_int32), ("waiting", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("launches", "fast_path", "slow_path", "token_requests", "host_syncs",
                                           "segments", "acct_kernels", "gpu_ns", "mem_used", "mem_limit",
@@ -86,6 +92,7 @@ def lib():
         "gemhook_pool_acquire": (d, [vp, C.c_int, d, d]),
         "gemhook_pool_release": (None, [vp, C.c_int]),
         "gemhook_pool_expire_token": (None, [vp]),
+        "gemhook_pool_slot_info": (C.c_int, [vp, C.c_int, C.POINTER(SlotInfo)]),
         "gemhook_pool_attach": (C.c_int, [vp, C.c_int]), "gemhook_pool_detach": (None, [vp]),
         "gemhook_pool_reap": (C.c_int, [vp]),
         "gemhook_pool_pod_launch": (C.c_int, [vp, C.c_int, i64, d, d, pd, pd, pd]),

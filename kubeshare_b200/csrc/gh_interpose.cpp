@@ -200,6 +200,86 @@ GH_SYNC_COPY(cuMemcpyDtoH_v2_ptds, (dtoh_fn)LATE(p_dtoh_ptds, "cuMemcpyDtoH_v2_p
 GH_SYNC_COPY(cuMemcpyHtoA_v2_ptds, (htoa_fn)LATE(p_htoa_ptds, "cuMemcpyHtoA_v2_ptds"), (CUarray dst, size_t off, const void* src, size_t n), (dst, off, src, n))
 GH_SYNC_COPY(cuMemcpyHtoD_v2_ptds, (htod_fn)LATE(p_htod_ptds, "cuMemcpyHtoD_v2_ptds"), (CUdeviceptr dst, const void* src, size_t n), (dst, src, n))
 
+// ---- modern entry points the reference never saw ------------------------------------------
+// Stream-ordered allocations are charged like cuMemAlloc; graph launches pass the token gate like a kernel
+// launch; cuStreamSynchronize / cuEventSynchronize count as host syncs only with GEMHOOK_EXTRA_HOOKS=1 (the
+// reference's burst detection knows cuCtxSynchronize and the four blocking copies only, hook.cpp:696-722).
+typedef CUresult(CUDAAPI* allocasync_fn)(CUdeviceptr*, size_t, CUstream);
+typedef CUresult(CUDAAPI* allocpool_fn)(CUdeviceptr*, size_t, CUmemoryPool, CUstream);
+typedef CUresult(CUDAAPI* freeasync_fn)(CUdeviceptr, CUstream);
+typedef CUresult(CUDAAPI* graphlaunch_fn)(CUgraphExec, CUstream);
+typedef CUresult(CUDAAPI* streamsync_fn)(CUstream);
+typedef CUresult(CUDAAPI* eventsync_fn)(CUevent);
+static void *p_allocasync, *p_allocasync_pt, *p_allocpool, *p_allocpool_pt, *p_freeasync, *p_freeasync_pt;
+static void *p_graphlaunch, *p_graphlaunch_pt, *p_streamsync, *p_streamsync_pt, *p_eventsync;
+
+#define GH_ALLOC_ASYNC(name, slot, sym)                                        \
+  GH_HOOK name(CUdeviceptr* dptr, size_t bytesize, CUstream hStream) {         \
+    if (!gh_mem_reserve(bytesize)) return CUDA_ERROR_OUT_OF_MEMORY;            \
+    CUresult r = ((allocasync_fn)LATE(slot, sym))(dptr, bytesize, hStream);    \
+    if (r != CUDA_SUCCESS) {                                                   \
+      gh_mem_unreserve(bytesize);                                              \
+      return r;                                                                \
+    }                                                                          \
+    gh_mem_commit((uint64_t)*dptr, bytesize);                                  \
+    return r;                                                                  \
+  }
+GH_ALLOC_ASYNC(cuMemAllocAsync, p_allocasync, "cuMemAllocAsync")
+GH_ALLOC_ASYNC(cuMemAllocAsync_ptsz, p_allocasync_pt, "cuMemAllocAsync_ptsz")
+
+#define GH_ALLOC_POOL(name, slot, sym)                                                  \
+  GH_HOOK name(CUdeviceptr* dptr, size_t bytesize, CUmemoryPool pool, CUstream hStream) { \
+    if (!gh_mem_reserve(bytesize)) return CUDA_ERROR_OUT_OF_MEMORY;                     \
+    CUresult r = ((allocpool_fn)LATE(slot, sym))(dptr, bytesize, pool, hStream);        \
+    if (r != CUDA_SUCCESS) {                                                            \
+      gh_mem_unreserve(bytesize);                                                       \
+      return r;                                                                         \
+    }                                                                                   \
+    gh_mem_commit((uint64_t)*dptr, bytesize);                                           \
+    return r;                                                                           \
+  }
+GH_ALLOC_POOL(cuMemAllocFromPoolAsync, p_allocpool, "cuMemAllocFromPoolAsync")
+GH_ALLOC_POOL(cuMemAllocFromPoolAsync_ptsz, p_allocpool_pt, "cuMemAllocFromPoolAsync_ptsz")
+
+GH_HOOK cuMemFreeAsync(CUdeviceptr dptr, CUstream hStream) {
+  gh_mem_free_key((uint64_t)dptr);
+  return ((freeasync_fn)LATE(p_freeasync, "cuMemFreeAsync"))(dptr, hStream);
+}
+GH_HOOK cuMemFreeAsync_ptsz(CUdeviceptr dptr, CUstream hStream) {
+  gh_mem_free_key((uint64_t)dptr);
+  return ((freeasync_fn)LATE(p_freeasync_pt, "cuMemFreeAsync_ptsz"))(dptr, hStream);
+}
+GH_HOOK cuGraphLaunch(CUgraphExec g, CUstream hStream) {
+  launch_gate(hStream);
+  return ((graphlaunch_fn)LATE(p_graphlaunch, "cuGraphLaunch"))(g, hStream);
+}
+GH_HOOK cuGraphLaunch_ptsz(CUgraphExec g, CUstream hStream) {
+  launch_gate(hStream);
+  return ((graphlaunch_fn)LATE(p_graphlaunch_pt, "cuGraphLaunch_ptsz"))(g, hStream);
+}
+static inline bool extra_syncs(void) { return gh_live_get() && gh_cfg.extra_hooks; }
+GH_HOOK cuStreamSynchronize(CUstream hStream) {
+  bool x = extra_syncs();
+  if (x) gh_host_sync_pre();
+  CUresult r = ((streamsync_fn)LATE(p_streamsync, "cuStreamSynchronize"))(hStream);
+  if (x && r == CUDA_SUCCESS) gh_host_sync_post();
+  return r;
+}
+GH_HOOK cuStreamSynchronize_ptsz(CUstream hStream) {
+  bool x = extra_syncs();
+  if (x) gh_host_sync_pre();
+  CUresult r = ((streamsync_fn)LATE(p_streamsync_pt, "cuStreamSynchronize_ptsz"))(hStream);
+  if (x && r == CUDA_SUCCESS) gh_host_sync_post();
+  return r;
+}
+GH_HOOK cuEventSynchronize(CUevent ev) {
+  bool x = extra_syncs();
+  if (x) gh_host_sync_pre();
+  CUresult r = ((eventsync_fn)LATE(p_eventsync, "cuEventSynchronize"))(ev);
+  if (x && r == CUDA_SUCCESS) gh_host_sync_post();
+  return r;
+}
+
 // ---- symbol tables ---------------------------------------------------------------------------------------
 extern "C" __attribute__((visibility("default"))) void* dlsym(void* handle, const char* symbol);
 GH_HOOK cuGetProcAddress_v2(const char* symbol, void** pfn, int cudaVersion, cuuint64_t flags,
@@ -233,6 +313,12 @@ static const HookEntry kHooks[] = {
     {"cuMemcpyDtoH_v2", "cuMemcpyDtoH", (void*)&cuMemcpyDtoH_v2, (void*)&cuMemcpyDtoH_v2_ptds},
     {"cuMemcpyHtoA_v2", "cuMemcpyHtoA", (void*)&cuMemcpyHtoA_v2, (void*)&cuMemcpyHtoA_v2_ptds},
     {"cuMemcpyHtoD_v2", "cuMemcpyHtoD", (void*)&cuMemcpyHtoD_v2, (void*)&cuMemcpyHtoD_v2_ptds},
+    {"cuMemAllocAsync", "cuMemAllocAsync", (void*)&cuMemAllocAsync, (void*)&cuMemAllocAsync_ptsz},
+    {"cuMemAllocFromPoolAsync", "cuMemAllocFromPoolAsync", (void*)&cuMemAllocFromPoolAsync, (void*)&cuMemAllocFromPoolAsync_ptsz},
+    {"cuMemFreeAsync", "cuMemFreeAsync", (void*)&cuMemFreeAsync, (void*)&cuMemFreeAsync_ptsz},
+    {"cuGraphLaunch", "cuGraphLaunch", (void*)&cuGraphLaunch, (void*)&cuGraphLaunch_ptsz},
+    {"cuStreamSynchronize", "cuStreamSynchronize", (void*)&cuStreamSynchronize, (void*)&cuStreamSynchronize_ptsz},
+    {"cuEventSynchronize", "cuEventSynchronize", (void*)&cuEventSynchronize, nullptr},
 };
 static const size_t kNumHooks = sizeof(kHooks) / sizeof(kHooks[0]);
 
@@ -241,7 +327,9 @@ static const char* const kHookedNames[] = {
     "cuLaunchKernelEx", "cuMemAlloc_v2", "cuMemAllocManaged", "cuMemAllocPitch_v2", "cuMemFree_v2",
     "cuArrayCreate_v2", "cuArray3DCreate_v2", "cuMipmappedArrayCreate", "cuArrayDestroy",
     "cuMipmappedArrayDestroy", "cuMemGetInfo_v2", "cuDeviceTotalMem_v2", "cuCtxSynchronize",
-    "cuMemcpyAtoH_v2", "cuMemcpyDtoH_v2", "cuMemcpyHtoA_v2", "cuMemcpyHtoD_v2", nullptr};
+    "cuMemcpyAtoH_v2", "cuMemcpyDtoH_v2", "cuMemcpyHtoA_v2", "cuMemcpyHtoD_v2",
+    "cuMemAllocAsync", "cuMemAllocFromPoolAsync", "cuMemFreeAsync", "cuGraphLaunch", "cuStreamSynchronize",
+    "cuEventSynchronize", nullptr};
 
 extern "C" __attribute__((visibility("default"))) const char* const* gemhook_hooked_symbols(size_t* count) {
   if (count) *count = sizeof(kHookedNames) / sizeof(kHookedNames[0]) - 1;
@@ -263,7 +351,12 @@ void* dlsym(void* handle, const char* symbol) {
         {"cuMemcpyAtoH_v2_ptds", (void*)&cuMemcpyAtoH_v2_ptds},
         {"cuMemcpyDtoH_v2_ptds", (void*)&cuMemcpyDtoH_v2_ptds},
         {"cuMemcpyHtoA_v2_ptds", (void*)&cuMemcpyHtoA_v2_ptds},
-        {"cuMemcpyHtoD_v2_ptds", (void*)&cuMemcpyHtoD_v2_ptds}};
+        {"cuMemcpyHtoD_v2_ptds", (void*)&cuMemcpyHtoD_v2_ptds},
+        {"cuMemAllocAsync_ptsz", (void*)&cuMemAllocAsync_ptsz},
+        {"cuMemAllocFromPoolAsync_ptsz", (void*)&cuMemAllocFromPoolAsync_ptsz},
+        {"cuMemFreeAsync_ptsz", (void*)&cuMemFreeAsync_ptsz},
+        {"cuGraphLaunch_ptsz", (void*)&cuGraphLaunch_ptsz},
+        {"cuStreamSynchronize_ptsz", (void*)&cuStreamSynchronize_ptsz}};
     for (size_t i = 0; i < sizeof(twins) / sizeof(twins[0]); i++)
       if (!strcmp(symbol, twins[i].n)) return twins[i].f;
   }

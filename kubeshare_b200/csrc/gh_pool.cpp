@@ -728,6 +728,25 @@ GH_EXPORT void gemhook_pool_mem_info(const gemhook_pool* p, int slot, uint64_t* 
   if (used) *used = p->r->slots[slot].mem_used.load(std::memory_order_acquire);
   if (limit) *limit = p->r->slots[slot].mem_limit;
 }
+GH_EXPORT int gemhook_pool_slot_info(const gemhook_pool* p, int slot, gemhook_slot_info* out) {
+  if (!p || !out || slot < 0 || slot >= (int)p->r->h.nslots.load(std::memory_order_acquire)) return -1;
+  const Slot& s = p->r->slots[slot];
+  memset(out, 0, sizeof(*out));
+  snprintf(out->name, sizeof(out->name), "%s", s.name);
+  out->min_frac = s.min_frac;
+  out->max_frac = s.max_frac;
+  out->mem_limit = s.mem_limit;
+  out->mem_used = s.mem_used.load(std::memory_order_relaxed);
+  out->gpu_ns = s.gpu_ns.load(std::memory_order_relaxed);
+  out->launches = s.launches.load(std::memory_order_relaxed);
+  out->tokens = s.grants;
+  out->quota_ms = s.quota;
+  out->accumulated_ms = s.grants ? s.closed_ms + (s.last_end - s.last_start) : 0.0;
+  out->holds_token = p->r->h.holder == slot ? 1 : 0;
+  out->waiting = s.state.load(std::memory_order_relaxed) == ST_WAITING ? 1 : 0;
+  return 0;
+}
+
 void gh_pool_publish_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches) {
   p->r->slots[slot].gpu_ns.store(gpu_ns, std::memory_order_relaxed);
   p->r->slots[slot].launches.store(launches, std::memory_order_relaxed);

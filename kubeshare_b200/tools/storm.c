@@ -288,6 +288,32 @@ int main(int argc, char** argv) {
     free_gpa(c);
     cuMemFree(b);
     cuMemFree(a);
+  } else if (!strcmp(mode, "modern")) {
+    /* entry points newer than the reference: cuLaunchKernelEx, stream-ordered allocation, cuStreamSynchronize */
+    CUstream st;
+    CK(cuStreamCreate(&st, CU_STREAM_NON_BLOCKING));
+    CUlaunchConfig cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDimX = cfg.gridDimY = cfg.gridDimZ = 1;
+    cfg.blockDimX = 32;
+    cfg.blockDimY = cfg.blockDimZ = 1;
+    cfg.hStream = st;
+    for (int b = 0; b < 5; b++) {
+      for (int i = 0; i < 20; i++) CK(cuLaunchKernelEx(&cfg, f_noop, NULL, NULL));
+      CK(cuStreamSynchronize(st));
+    }
+    CUdeviceptr a = 0, b2 = 0, c = 0;
+    CUresult r1 = cuMemAllocAsync(&a, 1000, st), r2 = cuMemAllocAsync(&b2, 2000, st), r3 = cuMemAllocAsync(&c, 3000, st);
+    size_t fr = 0, tot = 0;
+    cuMemGetInfo(&fr, &tot);
+    if (r2 == CUDA_SUCCESS) cuMemFreeAsync(b2, st);
+    CK(cuStreamSynchronize(st));
+    size_t fr2 = 0;
+    cuMemGetInfo(&fr2, &tot);
+    fprintf(out, "{\"mode\": \"modern\", \"rc\": [%d, %d, %d], \"free\": %zu, \"free_after\": %zu, \"total\": %zu}\n",
+            (int)r1, (int)r2, (int)r3, fr, fr2, tot);
+    if (r1 == CUDA_SUCCESS) cuMemFreeAsync(a, st);
+    CK(cuStreamSynchronize(st));
   } else if (!strcmp(mode, "probe")) {
     /* host cost (ns) of the building blocks; medians would be nicer, means over 20k are stable enough */
     const int N = 20000;

@@ -257,3 +257,6 @@ CUresult cuGetProcAddress(const char* symbol, void** pfn, int ver, cuuint64_t fl
   return *pfn ? CUDA_SUCCESS : CUDA_ERROR_NOT_FOUND;
 }
 CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { return CUDA_SUCCESS; }
+CUresult cuMemAllocAsync(CUdeviceptr* p, size_t bytes, CUstream s) { return fake_alloc(p, bytes); }
+CUresult cuMemAllocFromPoolAsync(CUdeviceptr* p, size_t bytes, CUmemoryPool pool, CUstream s) { return fake_alloc(p, bytes); }
+CUresult cuMemFreeAsync(CUdeviceptr p, CUstream s) { return cuMemFree_v2(p); }

@@ -128,3 +128,29 @@ def test_legacy_tcp_client_and_native_pool_client_share_one_token():
             legacy.close()
         finally:
             a.close()
+
+
+def test_poolctl_usage_export():
+    """per-client usage out of the pool, JSON and Prometheus text."""
+    ctl = os.path.join(kb.HERE, "bin", "gem-poolctl")
+    with tempfile.TemporaryDirectory() as tmp:
+        pool, qf = os.path.join(tmp, "pool"), os.path.join(tmp, "q.txt")
+        with open(qf, "w") as f:
+            f.write("2\nns/a 1.0 0.5 1000\nns/b 1.0 0.25 2000\n")   # kubeshare-config order: limit request
+        assert sp.check_output([ctl, pool, "load", qf, "limit_request"]).strip() == b"2"
+        L = kb.lib()
+        p = L.gemhook_pool_open(pool.encode(), 0, 0, 0, 0, 0)
+        assert L.gemhook_pool_mem_reserve(p, 1, 1234) == 1
+        q = L.gemhook_pool_acquire(p, 0, 0.0, 0.0)
+        assert q == 300.0
+        info = kb.SlotInfo()
+        assert L.gemhook_pool_slot_info(p, 1, info) == 0
+        assert (info.name, info.min_frac, info.max_frac, info.mem_used, info.mem_limit) == (b"ns/b", 0.25, 1.0, 1234, 2000)
+        dump = json.loads(sp.check_output([ctl, pool, "dump"]))
+        assert [d["pod"] for d in dump] == ["ns/a", "ns/b"]
+        assert (dump[0]["request"], dump[0]["limit"], dump[0]["tokens"], dump[0]["holds_token"]) == (0.5, 1.0, 1, 1)
+        assert dump[1]["mem_used"] == 1234
+        prom = sp.check_output([ctl, pool, "prom"]).decode()
+        assert 'gemhook_mem_used_bytes{pod="ns/b",request="0.25",limit="1"} 1234' in prom
+        assert 'gemhook_token_seconds_total{pod="ns/a"} 0.300000' in prom
+        L.gemhook_pool_close(p)

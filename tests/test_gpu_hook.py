@@ -207,3 +207,13 @@ def test_reference_hook_served_by_gem_arbiter_next_to_a_native_client():
         finally:
             arb.kill()
             arb.wait()
+
+
+def test_modern_entry_points_on_real_driver():
+    """cuLaunchKernelEx + cuMemAllocAsync/cuMemFreeAsync + cuStreamSynchronize against the real libcuda."""
+    with tempfile.TemporaryDirectory() as tmp:
+        res = storm(env_pool(tmp, quota="1\nbench/c0 1.0 1.0 5000\n", GEMHOOK_EXTRA_HOOKS=1), "--mode", "modern")
+        st = stats(tmp)[0]
+    assert st["launches"] == 100 and res["rc"] == [0, 0, 2]
+    assert (res["free"], res["free_after"], res["total"]) == (2000, 4000, 5000)
+    assert st["slow_path"] >= 5 and st["gpu_ns"] == st["gpu_ns_host"]

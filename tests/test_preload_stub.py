@@ -292,3 +292,19 @@ def test_two_clients_share_one_token_through_the_pool():
         acc = [L.gemhook_pool_accumulated_ms(p, k) for k in range(2)]
         assert all(a > 0 for a in acc)
         L.gemhook_pool_close(p)
+
+
+def test_modern_entry_points_are_gated_and_capped():
+    """cuLaunchKernelEx passes the token gate, stream-ordered allocations count against gpu_mem,
+    cuStreamSynchronize is a burst edge only when GEMHOOK_EXTRA_HOOKS=1."""
+    for extra, min_syncs, max_syncs in ((0, 0, 1), (1, 6, 12)):
+        with tempfile.TemporaryDirectory() as tmp:
+            env = hooked_env(tmp, quota="1\nbench/c0 1.0 1.0 5000\n", GEMHOOK_EXTRA_HOOKS=extra)
+            res = run_storm(env, "--mode", "modern")
+            st = stats_files(tmp)[0]
+            assert st["launches"] == 100
+            assert res["rc"] == [0, 0, 2] and (res["free"], res["total"]) == (2000, 5000)
+            assert res["free_after"] == 4000        # cuMemFreeAsync gave the 2000 bytes back
+            assert st["allocs_denied"] == 1 and st["mem_used"] == 0
+            assert min_syncs <= st["host_syncs"] <= max_syncs, st["host_syncs"]
+            assert (st["slow_path"] >= 5) == bool(extra)   # every burst edge seen only with the extra hooks
