@@ -22,7 +22,7 @@
 //   * block epilogue: columns are folded with __shfl_down_sync, warps are folded through shared
 //     memory, and ONE atomicAdd per (slot, field) per block goes to the device-resident totals;
 //   * the last block to finish (threadfence + ticket) publishes the running totals to the mapped
-//     pinned totals page with plain stores and bumps its sequence word (host side is a seqlock reader).
+//     pinned totals page: double-buffered by epoch parity, one system fence, then the epoch store.
 //
 // Build: nvcc -cubin -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (csrc/Makefile); the cubin
 // is embedded in libgemhook.so.1 and loaded with cuModuleLoadData (no cudart dependency).
@@ -39,12 +39,12 @@
 
 extern "C" {
 
+#define GEMHOOK_PAGE_MAX_SLOTS 64
 struct gemhook_totals_page {   // mapped pinned page (host reads it without any CUDA call)
-  unsigned long long seq;      // even = stable, odd = being written (seqlock)
-  unsigned long long epoch;    // number of reduce launches published
+  unsigned long long epoch;    // number of reduce launches published; buf[epoch & 1] holds the current totals
   unsigned long long nslots;
-  unsigned long long reserved;
-  unsigned long long v[1];     // [nslots][3]: elapsed_ns, launches, records
+  unsigned long long reserved[2];
+  unsigned long long buf[2][GEMHOOK_PAGE_MAX_SLOTS * 3];  // [slot][3]: elapsed_ns, launches, records
 };
 
 __device__ __forceinline__ uint4 ld_stream_16(const uint4* p) {
@@ -157,34 +157,27 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigne
     if (is_last) *ticket = 0u;  // self-reset for the next launch (stream-ordered)
   }
   __syncthreads();
-#ifdef GEMHOOK_EXP_NO_PUBLISH
-  if (0) {
-#else
   if (is_last && page) {
-#endif
-    // dev_totals[nslots*3] is the device-resident publish counter: no read ever crosses PCIe
+    // Double-buffered publication: the totals go to the buffer the host is NOT reading (epoch parity), ONE
+    // system-scope fence orders them before the 8-byte epoch store that flips the reader over.  (A seqlock would
+    // need three fences across PCIe; the reader-side rule is in gh_acct.cpp read_page.)  The publish counter lives
+    // in device memory (dev_totals[nslots*3]) so nothing is ever READ over PCIe here.
     __shared__ unsigned long long e_sh;
     __threadfence();
-    if (threadIdx.x == 0) {
-      unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(dev_totals + nslots * 3u) + 1ull;
-      e_sh = e;
-      *reinterpret_cast<volatile unsigned long long*>(&page->seq) = 2ull * e - 1ull;  // odd: writer active
-      __threadfence_system();
-    }
+    if (threadIdx.x == 0) e_sh = *reinterpret_cast<volatile unsigned long long*>(dev_totals + nslots * 3u) + 1ull;
     __syncthreads();
+    const unsigned long long e = e_sh;
+    unsigned long long* dst = page->buf[e & 1ull];
     for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
       // read through L2 (the atomics above were resolved there); volatile avoids a stale L1 line
-      page->v[t] = *reinterpret_cast<volatile unsigned long long*>(dev_totals + t);
+      dst[t] = *reinterpret_cast<volatile unsigned long long*>(dev_totals + t);
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-      unsigned long long e = e_sh;
       dev_totals[nslots * 3u] = e;
       page->nslots = nslots;
-      page->epoch = e;
-      __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(&page->seq) = 2ull * e;
+      *reinterpret_cast<volatile unsigned long long*>(&page->epoch) = e;
     }
   }
 }

@@ -25,11 +25,10 @@ extern const unsigned char _binary_acct_kernels_cubin_end[];
 namespace {
 
 struct totals_page {  // mirrors gemhook_totals_page in acct_kernels.cu
-  volatile uint64_t seq;
   volatile uint64_t epoch;
   volatile uint64_t nslots;
-  uint64_t reserved;
-  volatile uint64_t v[GEMHOOK_MAX_SLOTS * 3];
+  uint64_t reserved[2];
+  volatile uint64_t buf[2][GEMHOOK_MAX_SLOTS * 3];
 };
 
 const unsigned BIN_BYTES_PER_SLOT = 32u * 20u;  // GEMHOOK_BIN_BYTES_PER_SLOT
@@ -195,17 +194,21 @@ GH_EXPORT int gemhook_acct_reduce_device(gemhook_acct* a, uint64_t d_records, si
 }
 
 static int read_page(gemhook_acct* a, uint64_t* totals_out, uint64_t* epoch_out) {
-  // seqlock reader over the mapped pinned page: retry while the device is mid-publish
+  // The device writes buf[(e+1) & 1] and then stores epoch = e+1.  A copy of buf[e & 1] taken while the epoch
+  // moved from e to e+1 is still intact (the writer touched the other buffer); only a move of two or more
+  // may have overwritten it -> retry.
   for (int tries = 0; tries < 1000000; tries++) {
-    uint64_t s0 = a->page->seq;
+    uint64_t e1 = a->page->epoch;
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
-    if (s0 & 1u) continue;
-    uint64_t ep = a->page->epoch;
-    if (totals_out)
-      for (uint32_t i = 0; i < a->nslots * 3; i++) totals_out[i] = a->page->v[i];
+    if (totals_out) {
+      if (e1 == 0) memset(totals_out, 0, sizeof(uint64_t) * a->nslots * 3);
+      else
+        for (uint32_t i = 0; i < a->nslots * 3; i++) totals_out[i] = a->page->buf[e1 & 1][i];
+    }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
-    if (a->page->seq == s0) {
-      if (epoch_out) *epoch_out = ep;
+    uint64_t e2 = a->page->epoch;
+    if (e2 - e1 <= 1) {
+      if (epoch_out) *epoch_out = e1;
       return 0;
     }
   }
@@ -239,8 +242,7 @@ GH_EXPORT int gemhook_acct_reduce_host(gemhook_acct* a, const gemhook_record* re
     rc = -1;
   }
   if (rc == 0 && totals_out) {
-    if (n == 0 && a->page->epoch == 0) memset(totals_out, 0, sizeof(uint64_t) * a->nslots * 3);
-    else rc = read_page(a, totals_out, nullptr);
+    rc = read_page(a, totals_out, nullptr);
   }
   pthread_mutex_unlock(&a->mu);
   return rc;
@@ -260,7 +262,7 @@ GH_EXPORT int gemhook_acct_reset(gemhook_acct* a) {
   CUresult r = GH_CALL(cuLaunchKernel, a->f_clear, 1, 1, 1, 256, 1, 1, 0, a->stream, args, nullptr);
   if (r == CUDA_SUCCESS) a->kernel_launches.fetch_add(1, std::memory_order_relaxed);
   if (r == CUDA_SUCCESS) r = GH_CALL(cuStreamSynchronize, a->stream);
-  for (uint32_t i = 0; i < a->nslots * 3; i++) a->page->v[i] = 0;
+  for (uint32_t i = 0; i < a->nslots * 3; i++) a->page->buf[0][i] = a->page->buf[1][i] = 0;
   pthread_mutex_unlock(&a->mu);
   if (r != CUDA_SUCCESS) {
     gh_set_error("reset failed: %d", (int)r);

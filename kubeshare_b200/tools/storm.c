@@ -76,6 +76,26 @@ static void barrier(const char* dir, int id, int n, const char* tag) {
 
 static CUfunction f_noop, f_spin, f_conv;
 
+/* multi-threaded client: every thread launches on its own stream and synchronises now and then */
+#include <pthread.h>
+struct mt_arg { CUcontext ctx; long launches; int id; };
+static void* mt_worker(void* p) {
+  struct mt_arg* a = (struct mt_arg*)p;
+  CUstream st;
+  CK(cuCtxSetCurrent(a->ctx));
+  CK(cuStreamCreate(&st, CU_STREAM_DEFAULT));
+  for (long i = 1; i <= a->launches; i++) {
+    CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, (i & 1) ? st : NULL, NULL, NULL));
+    if (i % (97 + a->id * 13) == 0) CK(cuCtxSynchronize());
+    if (i % 1000 == 0) {
+      CUdeviceptr d;
+      if (cuMemAlloc(&d, 4096 + a->id) == CUDA_SUCCESS) cuMemFree(d);
+    }
+  }
+  CK(cuCtxSynchronize());
+  return NULL;
+}
+
 int main(int argc, char** argv) {
   const char* mode = "storm";
   long step_launches = 65536, sync_every = 1024, steps = 16, warmup = 3, rounds = 2000;
@@ -288,6 +308,19 @@ int main(int argc, char** argv) {
     free_gpa(c);
     cuMemFree(b);
     cuMemFree(a);
+  } else if (!strcmp(mode, "mt")) {
+    int T = nclients > 1 ? nclients : 4;  /* --nclients doubles as thread count here */
+    pthread_t tid[64];
+    struct mt_arg args[64];
+    double t0 = now_s();
+    for (int i = 0; i < T && i < 64; i++) {
+      args[i].ctx = ctx;
+      args[i].launches = step_launches;
+      args[i].id = i;
+      pthread_create(&tid[i], NULL, mt_worker, &args[i]);
+    }
+    for (int i = 0; i < T && i < 64; i++) pthread_join(tid[i], NULL);
+    fprintf(out, "{\"mode\": \"mt\", \"threads\": %d, \"launches\": %ld, \"wall_s\": %.6f}\n", T, (long)T * step_launches, now_s() - t0);
   } else if (!strcmp(mode, "modern")) {
     /* entry points newer than the reference: cuLaunchKernelEx, stream-ordered allocation, cuStreamSynchronize */
     CUstream st;

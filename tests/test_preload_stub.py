@@ -308,3 +308,16 @@ def test_modern_entry_points_are_gated_and_capped():
             assert st["allocs_denied"] == 1 and st["mem_used"] == 0
             assert min_syncs <= st["host_syncs"] <= max_syncs, st["host_syncs"]
             assert (st["slow_path"] >= 5) == bool(extra)   # every burst edge seen only with the extra hooks
+
+
+def test_multithreaded_client_no_lost_launches_no_deadlock():
+    """8 application threads launching on their own streams, syncing and allocating concurrently."""
+    with tempfile.TemporaryDirectory() as tmp:
+        env = hooked_env(tmp, GEMHOOK_BASE_QUOTA_MS=10, GEMHOOK_MIN_QUOTA_MS=2, GEMHOOK_SEG_MIN_US=100)
+        res = run_storm(env, "--mode", "mt", "--nclients", 8, "--step-launches", 20000, timeout=120)
+        st = stats_files(tmp)[0]
+        stub = json.load(open(os.path.join(tmp, "stub.json")))
+        assert res["launches"] == st["launches"] == 160000
+        assert stub["launches"] >= 160000          # + our own reduce launches
+        assert st["mem_used"] == 0 and st["allocs_denied"] == 0
+        assert st["token_requests"] >= 3
