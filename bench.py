@@ -127,10 +127,38 @@ def free_ports(n):
     return ports
 
 
+_PHYS = None
+
+
+def physical_cores():
+    """One logical CPU per physical core (first hyper-thread sibling), so pinned clients never share a core."""
+    global _PHYS
+    if _PHYS is None:
+        seen, out = set(), []
+        try:
+            avail = sorted(os.sched_getaffinity(0))
+        except AttributeError:
+            avail = list(range(os.cpu_count() or 1))
+        for c in avail:
+            try:
+                sib = open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c).read().strip()
+            except OSError:
+                sib = str(c)
+            if sib not in seen:
+                seen.add(sib)
+                out.append(c)
+        _PHYS = out or avail
+    return _PHYS
+
+
 def pin(core):
+    """`core` is an index into the list of physical cores (wraps around)."""
+    phys = physical_cores()
+    cpu = phys[core % len(phys)]
+
     def f():
         try:
-            os.sched_setaffinity(0, {core % os.cpu_count()})
+            os.sched_setaffinity(0, {cpu})
         except OSError:
             pass
     return f
@@ -334,8 +362,9 @@ def main():
         return
 
     ncpu = os.cpu_count() or 1
-    cores_per_rank = max(1, ncpu // max(world, 1))
-    core_base = rank * cores_per_rank + 1
+    nphys = len(physical_cores())
+    cores_per_rank = max(1, nphys // max(n_gpus_reported, 1))
+    core_base = rank * cores_per_rank + 1  # indices into physical_cores(): ranks never share a physical core
     sweep = sorted({int(c) for c in args.clients.split(",") if c} | {args.headline_clients})
     sampler = ClockSampler(gpu)
     sampler.start()
@@ -421,7 +450,7 @@ def main():
         "hook_stats": {str(c): [{k: s.get(k) for k in ("token_requests", "token_wait_ms", "slow_path", "segments", "acct_kernels", "gpu_ns", "accumulated_token_ms", "quota_ms")}
                                  for r in allr for s in r[c]["hooked"].get("stats", [])] for c in sweep},
         "gpu_launches": int(acct_kernels + (roof or {}).get("kernel_launches", 0)) if mode == "ours" else 0,
-        "clocks": clocks, "host": {"cpus": ncpu, "client_cores": "one pinned core per client, daemons on their own cores"},
+        "clocks": clocks, "host": {"cpus": ncpu, "physical_cores": nphys, "client_cores": "one pinned PHYSICAL core per client (no hyper-thread siblings shared), daemons on their own cores"},
         "wall_s": time.time() - t_start,
     }
     if mode == "ours":

@@ -100,7 +100,7 @@ def main():
     out = {"config": "configs[4]: %d x B200, 4 clients/device, min-fractions %s, limit 1.0, mnist-shaped conv, %d iterations x 100 launches + DtoH"
                      % (args.gpus, FRACS, args.iters)}
     impls = ["unhooked", "ours", "reference"] if args.impl == "both" else [args.impl]
-    ncpu = os.cpu_count() or 1
+    ncpu = len(bench.physical_cores())
     for impl in impls:
         if impl == "reference" and not os.path.exists(os.path.join(bench.REFDIR, "libgemhook_ref.so.1")):
             continue
