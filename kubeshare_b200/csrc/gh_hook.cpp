@@ -84,6 +84,8 @@ struct gh_live {
 
   // staging of records (pinned, double buffered)
   gemhook_record* stage[2] = {nullptr, nullptr};
+  CUevent stage_done[2] = {nullptr, nullptr};  // recorded on the accounting stream after each buffer's copy
+  bool stage_inflight[2] = {false, false};
   uint32_t stage_cap = 0, stage_n = 0;
   int stage_cur = 0;
 
@@ -201,14 +203,24 @@ static void stage_record(gh_live* L, uint32_t launches, uint64_t ns) {
 static void flush_stage_locked(gh_live* L, bool force) {
   if (!L->acct || L->stage_n == 0) return;
   if (!force && L->stage_n < gh_cfg.flush_records) return;
-  // the other buffer's copy was issued at least one flush ago on the same stream: make sure it is done
-  gh_acct_push_async(L->acct, L->stage[L->stage_cur], L->stage_n);
-  L->stage_cur ^= 1;
+  int b = L->stage_cur;
+  if (gh_acct_push_async(L->acct, L->stage[b], L->stage_n) == 0 && L->stage_done[b]) {
+    CUstream as = (CUstream)(uintptr_t)gemhook_acct_stream(L->acct);
+    L->stage_inflight[b] = GH_CALL(cuEventRecord, L->stage_done[b], as) == CUDA_SUCCESS;
+  }
+  L->stage_cur = b ^ 1;
   L->stage_n = 0;
-  if (force) gemhook_acct_sync(L->acct);
+  // the buffer we switch to was handed to the copy engine one flush ago: it must be done before we overwrite it
+  // (it always is in practice -- a flush happens every GEMHOOK_FLUSH_RECORDS segments -- so this never blocks)
+  if (L->stage_inflight[b ^ 1]) {
+    GH_CALL(cuEventSynchronize, L->stage_done[b ^ 1]);
+    L->stage_inflight[b ^ 1] = false;
+  }
+  if (force) {
+    gemhook_acct_sync(L->acct);
+    L->stage_inflight[0] = L->stage_inflight[1] = false;
+  }
 }
-
-// (declared above)
 
 static void seg_begin_locked(gh_live* L, CUstream stream) {
   if (gh_cfg.dry_run || !L->cuda_ready) return;
@@ -426,6 +438,7 @@ static void cuda_init_locked(gh_live* L) {
         void* hp = nullptr;
         if (GH_CALL(cuMemHostAlloc, &hp, L->stage_cap * sizeof(gemhook_record), CU_MEMHOSTALLOC_PORTABLE) == CUDA_SUCCESS)
           L->stage[b] = (gemhook_record*)hp;
+        GH_CALL(cuEventCreate, &L->stage_done[b], CU_EVENT_DISABLE_TIMING);
       }
       if (L->pool) {
         // "shared-pinned": the credit pool is page-locked and device-mapped, so device code (and peers'

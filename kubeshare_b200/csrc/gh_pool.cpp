@@ -104,6 +104,7 @@ struct alignas(64) Header {
   uint64_t total_grants;
   uint32_t ledger_len;
   uint32_t ledger_dropped;
+  uint64_t boot_id;  // CLOCK_MONOTONIC restarts at boot: a pool file that survived a reboot is re-initialised
 };
 
 // one entry per attached process; byte 0 of each entry is covered by an OFD lock held by the owner for its
@@ -125,6 +126,17 @@ struct Region {
   Span ledger[LEDGER_CAP];
   Attach attach[MAX_ATTACH];
 };
+
+uint64_t boot_id_hash() {
+  uint64_t h = 1469598103934665603ULL;
+  FILE* f = fopen("/proc/sys/kernel/random/boot_id", "r");
+  if (f) {
+    int c;
+    while ((c = fgetc(f)) != EOF) h = (h ^ (uint64_t)(unsigned char)c) * 1099511628211ULL;
+    fclose(f);
+  }
+  return h ? h : 1;
+}
 
 long futex(std::atomic<uint32_t>* addr, int op, uint32_t val, const struct timespec* ts) {
   return syscall(SYS_futex, (uint32_t*)addr, op, val, ts, nullptr, 0);
@@ -382,6 +394,7 @@ GH_EXPORT gemhook_pool* gemhook_pool_open(const char* path, int create, double b
     h.window = window_ms;
     h.start_ns = start_ns ? start_ns : gh_now_ns();
     h.holder = -1;
+    h.boot_id = boot_id_hash();
     h.nslots.store(0);
     h.ready.store(1, std::memory_order_release);
   } else {
@@ -390,6 +403,36 @@ GH_EXPORT gemhook_pool* gemhook_pool_open(const char* path, int create, double b
       gh_set_error("%s is not an initialised gemhook credit pool", path);
       gemhook_pool_close(p);
       return nullptr;
+    }
+    if (h.boot_id != boot_id_hash()) {
+      // the file outlived a reboot (hostPath): its clock origin, token holder, ledger, attachments and byte
+      // counters describe processes that no longer exist.  Keep the configuration rows, drop the dynamic state.
+      h.lock.store(0);
+      p->lock();
+      if (h.boot_id != boot_id_hash()) {
+        uint32_t ns = h.nslots.load();
+        for (uint32_t i = 0; i < ns; i++) {
+          Slot& s = p->r->slots[i];
+          s.quota = h.base_quota;
+          s.burst = 0;
+          s.last_start = s.last_end = s.closed_ms = 0;
+          s.grants = 0;
+          s.state.store(ST_IDLE);
+          s.mem_used.store(0);
+          s.gpu_ns.store(0);
+          s.launches.store(0);
+          s.pod_quota = 0;
+          s.pod_token_us = 0;
+          s.pod_overuse = 0;
+        }
+        memset((void*)p->r->attach, 0, sizeof(p->r->attach));
+        h.ledger_len = 0;
+        h.holder = -1;
+        h.deadline_ms = 0;
+        h.start_ns = gh_now_ns();
+        h.boot_id = boot_id_hash();
+      }
+      p->unlock();
     }
   }
   return p;
