@@ -217,3 +217,35 @@ def test_modern_entry_points_on_real_driver():
     assert st["launches"] == 100 and res["rc"] == [0, 0, 2]
     assert (res["free"], res["free_after"], res["total"]) == (2000, 4000, 5000)
     assert st["slow_path"] >= 5 and st["gpu_ns"] == st["gpu_ns_host"]
+
+
+def test_pytorch_application_under_the_hook():
+    """A real cudart application (PyTorch): cudart binds the driver through dlsym + cuGetProcAddress_v2, both
+    interposed.  The gpu_mem cap shows up as torch's OOM, mem_get_info is virtualised, every kernel passes the gate."""
+    import sys
+
+    script = r'''
+import json, sys, torch
+x = torch.ones(1 << 20, device="cuda")
+for _ in range(1500):
+    x = x + 1
+torch.cuda.synchronize()
+free, total = torch.cuda.mem_get_info()
+big = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")      # 1 GiB fits under the 2 GiB cap
+oom = False
+try:
+    torch.empty(3 << 30, dtype=torch.uint8, device="cuda")          # 3 GiB does not
+except torch.cuda.OutOfMemoryError:
+    oom = True
+print(json.dumps({"x0": float(x[0]), "total": total, "free_le_total": free <= total, "oom": oom}))
+'''
+    with tempfile.TemporaryDirectory() as tmp:
+        env = env_pool(tmp, quota="1\nbench/c0 1.0 1.0 %d\n" % (2 << 30))
+        p = sp.run([sys.executable, "-c", script], env=env, stdout=sp.PIPE, stderr=sp.PIPE, timeout=300)
+        assert p.returncode == 0, p.stderr.decode()[-2000:]
+        res = json.loads(p.stdout.decode().strip().splitlines()[-1])
+        st = stats(tmp)[0]
+    assert res["x0"] == 1501.0 and res["oom"] is True
+    assert res["total"] == 2 << 30 and res["free_le_total"]
+    assert st["launches"] >= 1500 and st["allocs_denied"] >= 1
+    assert st["gpu_ns"] == st["gpu_ns_host"] > 0
