@@ -40,7 +40,9 @@ GH_EXPORT const char* gemhook_version(void) { return "gemhook-b200 0.1 (abi 1, s
 // glibc >= 2.34 no longer exports __libc_dlsym (what the reference used, hook.cpp:66-84); dlvsym with
 // the versioned name is the supported way to get the real dlsym from inside a dlsym interposer.
 typedef void* (*dlsym_fn)(void*, const char*);
-static dlsym_fn real_dlsym_ptr(void) {
+#define GH_NO_SANITIZE __attribute__((no_sanitize("thread", "address", "undefined")))
+// (sanitizer runtimes call dlsym() while they initialise: these two must not be instrumented)
+GH_NO_SANITIZE static dlsym_fn real_dlsym_ptr(void) {
   static dlsym_fn fn = nullptr;
   if (!fn) {
     fn = (dlsym_fn)dlvsym(RTLD_NEXT, "dlsym", "GLIBC_2.2.5");
@@ -48,7 +50,7 @@ static dlsym_fn real_dlsym_ptr(void) {
   }
   return fn;
 }
-void* gh_true_dlsym(void* handle, const char* symbol) {
+GH_NO_SANITIZE void* gh_true_dlsym(void* handle, const char* symbol) {
   dlsym_fn fn = real_dlsym_ptr();
   return fn ? fn(handle, symbol) : nullptr;
 }

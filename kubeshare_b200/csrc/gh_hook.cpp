@@ -29,7 +29,7 @@ int gh_acct_push_async(gemhook_acct* a, const gemhook_record* pinned_records, si
 void gh_pool_publish_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches);
 void* gh_pool_region(gemhook_pool* p, size_t* bytes);
 
-volatile uint32_t gh_gate_open = 0;
+uint32_t gh_gate_open = 0;  // accessed with relaxed __atomic builtins only (plain MOVs on x86, race-free by the book)
 uint64_t gh_launch_count = 0;
 uint32_t gh_seg_mask = 0xffffffffu;
 
@@ -43,7 +43,7 @@ struct gh_live {
   bool renewing = false;
   gemhook_gate* gate = nullptr;
   bool enabled = false;
-  bool cuda_ready = false;
+  std::atomic<bool> cuda_ready{false};
 
   // transport
   gemhook_pool* pool = nullptr;
@@ -92,7 +92,8 @@ struct gh_live {
   // stats
   std::atomic<uint64_t> slow_path{0}, token_requests{0}, host_syncs{0}, segments{0};
   uint64_t gpu_ns_host = 0;  // host-side running sum of the same records (cross-check of the device totals)
-  double token_wait_ms = 0, accumulated_token_ms = 0;
+  std::atomic<uint64_t> token_wait_ns{0};
+  double accumulated_token_ms = 0;
   int64_t last_token_ns = 0;
   double last_quota_ms = 0;
 };
@@ -127,7 +128,7 @@ static double token_from_scheduler(gh_live* L, double overuse_ms, double next_bu
     }
     q = rsp.quota_ms;
   }
-  L->token_wait_ms += (double)(gh_now_ns() - t0) / 1e6;
+  L->token_wait_ns.fetch_add((uint64_t)(gh_now_ns() - t0), std::memory_order_relaxed);
   GH_DEBUG("token: overuse %.3f ms, next burst %.3f ms -> quota %.3f ms", overuse_ms, next_burst_ms, q);
   return q;
 }
@@ -269,8 +270,11 @@ void gh_segment_tick(CUstream stream) {
 static void sync_pre(bool force) {
   gh_live* L = g_live;
   if (!L || !L->cuda_ready || gh_cfg.dry_run) return;
-  if (!L->seg_open && L->npending == 0 && L->stage_n < gh_cfg.flush_records) return;
   pthread_mutex_lock(&L->mu);
+  if (!L->seg_open && L->npending == 0 && L->stage_n < gh_cfg.flush_records) {
+    pthread_mutex_unlock(&L->mu);
+    return;
+  }
   int fresh = 0;
   bool old_enough = force || (gh_now_ns() - L->seg_begin_host_ns >= (int64_t)gh_cfg.seg_min_us * 1000);
   if (L->seg_open && !L->seg_end_recorded && !old_enough) {
@@ -329,7 +333,7 @@ static void resolve_pending_locked(gh_live* L, bool may_block, int skip_last) {
 
 static void host_sync_locked(gh_live* L, int64_t now) {
   gemhook_gate_host_sync(L->gate, now);
-  gh_gate_open = 0;
+  __atomic_store_n(&gh_gate_open, 0u, __ATOMIC_RELAXED);
   if (L->seg_open && L->seg_spans_sync && !L->seg_end_recorded) L->seg_sync_return_ns = now;  // merged: stays open
   else L->seg_open = false;
 }
@@ -367,7 +371,7 @@ static void live_init(void) {
   if (gh_cfg.disabled || gh_driver_init() != 0) {
     L->enabled = false;
     g_live = L;
-    gh_gate_open = 1;  // pass-through
+    __atomic_store_n(&gh_gate_open, 1u, __ATOMIC_RELAXED);  // pass-through
     return;
   }
   L->enabled = true;
@@ -399,7 +403,7 @@ static void live_init(void) {
     fatal_or_disable(L, "scheduler IP file missing (set GEMHOOK_SCHEDULER_IP or /kubeshare/library/schedulerIP.txt)");
   }
   g_live = L;
-  if (!L->enabled) gh_gate_open = 1;
+  if (!L->enabled) __atomic_store_n(&gh_gate_open, 1u, __ATOMIC_RELAXED);
   // registered after the driver's own atexit handlers (cuInit ran before the first intercepted call),
   // so it runs BEFORE them and CUDA is still usable for the final flush
   gh_register_exit_hook();
@@ -503,7 +507,7 @@ void gh_launch_slow(CUstream stream) {
   }
   gemhook_gate_launch_end(L->gate, gh_now_ns());
   seg_begin_locked(L, stream);
-  gh_gate_open = 1;
+  __atomic_store_n(&gh_gate_open, 1u, __ATOMIC_RELAXED);
   pthread_mutex_unlock(&L->mu);
 }
 
@@ -550,7 +554,7 @@ GH_EXPORT int gemhook_get_stats(gemhook_stats* out) {
   out->mem_used = out->mem_limit - out->mem_used;  // gh_mem_info returns (free, total)
   out->quota_ms = gemhook_gate_quota_ms(L->gate);
   out->overuse_ms = gemhook_gate_overuse_ms(L->gate);
-  out->token_wait_ms = L->token_wait_ms;
+  out->token_wait_ms = (double)L->token_wait_ns.load() / 1e6;
   out->accumulated_token_ms = L->accumulated_token_ms;
   return 0;
 }

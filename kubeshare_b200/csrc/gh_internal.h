@@ -75,7 +75,7 @@ gh_live* gh_live_get(void);  // lazily initialised process singleton (NULL if di
 void gh_launch_slow(CUstream stream);
 void gh_host_sync_pre(void);
 void gh_host_sync_post(void);
-extern volatile uint32_t gh_gate_open;     // 1: burst ongoing and token valid -> fast path
+extern uint32_t gh_gate_open;              // 1: burst ongoing and token valid -> fast path (relaxed atomics)
 extern uint64_t gh_launch_count;           // intercepted launches (relaxed)
 extern uint32_t gh_seg_mask;               // segment every (mask+1) launches; 0xffffffff = burst edges only
 void gh_segment_tick(CUstream stream);

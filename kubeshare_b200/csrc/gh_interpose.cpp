@@ -22,7 +22,7 @@ static void* resolve_late(void** slot, const char* name) {
 
 // ---- launches ------------------------------------------------------------------------------------------
 static inline __attribute__((always_inline)) void launch_gate(CUstream hStream) {
-  if (__builtin_expect(gh_gate_open != 0, 1)) {
+  if (__builtin_expect(__atomic_load_n(&gh_gate_open, __ATOMIC_RELAXED) != 0, 1)) {
     uint64_t n = __atomic_add_fetch(&gh_launch_count, 1, __ATOMIC_RELAXED);
     if (__builtin_expect(((uint32_t)n & gh_seg_mask) == 0, 0)) gh_segment_tick(hStream);
   } else {
@@ -337,7 +337,7 @@ extern "C" __attribute__((visibility("default"))) const char* const* gemhook_hoo
 }
 
 // dlsym interposer (hook.cpp:109-159): anything that is not a hooked driver symbol goes to the libc dlsym
-void* dlsym(void* handle, const char* symbol) {
+__attribute__((no_sanitize("thread", "address", "undefined"))) void* dlsym(void* handle, const char* symbol) {
   if (symbol && symbol[0] == 'c' && symbol[1] == 'u') {
     if (!strcmp(symbol, "cuGetProcAddress_v2")) return (void*)&cuGetProcAddress_v2;
     if (!strcmp(symbol, "cuGetProcAddress")) return (void*)&cuGetProcAddress;

@@ -548,19 +548,28 @@ GH_EXPORT double gemhook_pool_usage(gemhook_pool* p, int slot, double now_ms) {
   return usage[slot];
 }
 
-GH_EXPORT size_t gemhook_pool_history(const gemhook_pool* p, int* slots, double* starts, double* ends, size_t cap) {
+// Observers take the arbitration lock too: the ledger and the per-slot token fields are plain (non-atomic) data
+// owned by whoever holds it (ThreadSanitizer-clean, tests/test_sanitizers.py).
+GH_EXPORT size_t gemhook_pool_history(const gemhook_pool* cp, int* slots, double* starts, double* ends, size_t cap) {
+  gemhook_pool* p = const_cast<gemhook_pool*>(cp);
+  p->lock();
   size_t n = p->r->h.ledger_len;
   for (size_t i = 0; i < n && i < cap; i++) {
     if (slots) slots[i] = p->r->ledger[i].slot;
     if (starts) starts[i] = p->r->ledger[i].start;
     if (ends) ends[i] = p->r->ledger[i].end;
   }
+  p->unlock();
   return n;
 }
 
-GH_EXPORT double gemhook_pool_accumulated_ms(const gemhook_pool* p, int slot) {
+GH_EXPORT double gemhook_pool_accumulated_ms(const gemhook_pool* cp, int slot) {
+  gemhook_pool* p = const_cast<gemhook_pool*>(cp);
+  p->lock();
   const Slot& s = p->r->slots[slot];
-  return s.grants ? s.closed_ms + (s.last_end - s.last_start) : 0.0;
+  double v = s.grants ? s.closed_ms + (s.last_end - s.last_start) : 0.0;
+  p->unlock();
+  return v;
 }
 
 static int pod_launch_locked(gemhook_pool* p, int slot, int attach_idx, int64_t now_us, double overuse, double burst,
@@ -771,8 +780,10 @@ GH_EXPORT void gemhook_pool_mem_info(const gemhook_pool* p, int slot, uint64_t* 
   if (used) *used = p->r->slots[slot].mem_used.load(std::memory_order_acquire);
   if (limit) *limit = p->r->slots[slot].mem_limit;
 }
-GH_EXPORT int gemhook_pool_slot_info(const gemhook_pool* p, int slot, gemhook_slot_info* out) {
+GH_EXPORT int gemhook_pool_slot_info(const gemhook_pool* cp, int slot, gemhook_slot_info* out) {
+  gemhook_pool* p = const_cast<gemhook_pool*>(cp);
   if (!p || !out || slot < 0 || slot >= (int)p->r->h.nslots.load(std::memory_order_acquire)) return -1;
+  p->lock();
   const Slot& s = p->r->slots[slot];
   memset(out, 0, sizeof(*out));
   snprintf(out->name, sizeof(out->name), "%s", s.name);
@@ -787,6 +798,7 @@ GH_EXPORT int gemhook_pool_slot_info(const gemhook_pool* p, int slot, gemhook_sl
   out->accumulated_ms = s.grants ? s.closed_ms + (s.last_end - s.last_start) : 0.0;
   out->holds_token = p->r->h.holder == slot ? 1 : 0;
   out->waiting = s.state.load(std::memory_order_relaxed) == ST_WAITING ? 1 : 0;
+  p->unlock();
   return 0;
 }
 

@@ -1,0 +1,66 @@
+"""CPU: ThreadSanitizer / AddressSanitizer+UBSan runs of the host logic (the reference has known races, SURVEY.md 5:
+quota_time/overuse read without a lock, client_info_map replaced under readers).
+
+ * tests/native/pool_stress.cpp: 6 client threads + an observer hammering one credit pool and a gate.
+ * the whole libgemhook.so.1 built with -fsanitize=thread, preloaded (after libtsan) into the multi-threaded storm
+   client on the stub driver.
+Skipped when the toolchain has no sanitizer runtimes."""
+import glob
+import os
+import subprocess as sp
+import tempfile
+
+import pytest
+
+import kubeshare_b200 as kb
+
+CSRC = os.path.join(kb.HERE, "csrc")
+SRCS = ["gh_core.cpp", "gh_gate.cpp", "gh_wire.cpp", "gh_pool.cpp", "gh_mem.cpp", "gh_acct.cpp", "gh_hook.cpp", "gh_interpose.cpp"]
+GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def _runtime(name):
+    hits = glob.glob("/usr/lib/x86_64-linux-gnu/%s.so.*" % name) + glob.glob("/usr/lib/gcc/x86_64-linux-gnu/*/%s.so" % name)
+    return os.path.realpath(hits[0]) if hits else None
+
+
+def _build(out, san, sources, shared=False):
+    cmd = [GXX, "-std=c++17", "-O1", "-g", "-fsanitize=" + san, "-fno-omit-frame-pointer", "-Wno-tsan",
+           "-I/usr/local/cuda/include", *sources, "-o", out, "-ldl", "-lpthread"]
+    if shared:
+        cmd[1:1] = ["-fPIC", "-shared"]
+    p = sp.run(cmd, stdout=sp.PIPE, stderr=sp.PIPE)
+    if p.returncode != 0:
+        pytest.skip("sanitizer build unavailable: " + p.stderr.decode()[-300:])
+
+
+@pytest.mark.parametrize("san", ["thread", "address,undefined"])
+def test_pool_and_gate_under_sanitizers(san):
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "stress")
+        _build(exe, san, [os.path.join(kb.ROOT, "tests", "native", "pool_stress.cpp")] +
+               [os.path.join(CSRC, f) for f in ("gh_pool.cpp", "gh_core.cpp", "gh_gate.cpp")])
+        p = sp.run([exe, "6", "120"], stdout=sp.PIPE, stderr=sp.PIPE, timeout=300)
+        err = p.stderr.decode()
+        assert "Sanitizer" not in err and "runtime error" not in err, err[-3000:]
+        assert p.returncode == 0 and b'"violations": 0' in p.stdout
+
+
+def test_live_hook_is_tsan_clean_with_a_multithreaded_client():
+    tsan = _runtime("libtsan")
+    if not tsan:
+        pytest.skip("no libtsan runtime")
+    with tempfile.TemporaryDirectory() as tmp:
+        lib = os.path.join(tmp, "libgemhook_tsan.so")
+        _build(lib, "thread", [os.path.join(CSRC, f) for f in SRCS] + [os.path.join(CSRC, "build", "acct_cubin.o")], shared=True)
+        with open(os.path.join(tmp, "quota.txt"), "w") as f:
+            f.write("1\nbench/c0 1.0 1.0 8589934592\n")
+        env = {k: v for k, v in os.environ.items() if not k.startswith("GEMHOOK_")}
+        env.update(LD_LIBRARY_PATH=kb.STUB_DIR + ":" + env.get("LD_LIBRARY_PATH", ""), LD_PRELOAD=tsan + ":" + lib,
+                   GEMHOOK_POOL=os.path.join(tmp, "pool"), GEMHOOK_QUOTA_FILE=os.path.join(tmp, "quota.txt"), POD_NAME="bench/c0",
+                   GEMHOOK_BASE_QUOTA_MS="10", GEMHOOK_MIN_QUOTA_MS="2", GEMHOOK_SEG_MIN_US="100", GEMHOOK_SEG_LAUNCHES="64")
+        p = sp.run([kb.STORM_PATH, "--mode", "mt", "--nclients", "6", "--step-launches", "5000"], env=env, stdout=sp.PIPE,
+                   stderr=sp.PIPE, timeout=300)
+        err = p.stderr.decode()
+        assert "ThreadSanitizer" not in err, err[-3000:]
+        assert p.returncode == 0 and b'"launches": 30000' in p.stdout
