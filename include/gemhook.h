@@ -140,6 +140,9 @@ void gemhook_pool_close(gemhook_pool *);
  * gem-schd reads them (scheduler.cpp:205); swap_columns=1 reads them as kubeshare-config writes them
  * (limit request, pkg/config/query.go:56).  Returns client count, -1 on parse error. */
 int gemhook_pool_load_config(gemhook_pool *, const char *text, int swap_columns);
+/* stat the quota file and (re)load it only if it changed since the pool last saw it (gem-schd does this with
+ * inotify, scheduler.cpp:219-265). 1 = reloaded, 0 = unchanged, -1 = unreadable / malformed. */
+int gemhook_pool_sync_quota_file(gemhook_pool *, const char *path, int swap_columns);
 int gemhook_pool_find(const gemhook_pool *, const char *name); /* slot index or -1 */
 int gemhook_pool_nslots(const gemhook_pool *);
 /* token policy, clock injected (now_ms = ms since pool start_ns, as scheduler.cpp:107-109) */

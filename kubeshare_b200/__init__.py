@@ -83,6 +83,7 @@ def lib():
         "gemhook_predictor_predict_unmerged": (d, [vp, i64]), "gemhook_predictor_predict_merged": (d, [vp, i64]),
         "gemhook_pool_open": (vp, [cp, C.c_int, d, d, d, i64]), "gemhook_pool_close": (None, [vp]),
         "gemhook_pool_load_config": (C.c_int, [vp, cp, C.c_int]),
+        "gemhook_pool_sync_quota_file": (C.c_int, [vp, cp, C.c_int]),
         "gemhook_pool_find": (C.c_int, [vp, cp]), "gemhook_pool_nslots": (C.c_int, [vp]),
         "gemhook_pool_request": (C.c_int, [vp, C.c_int, d, d, d]),
         "gemhook_pool_schedule": (C.c_int, [vp, d, pi, pd, pd]),

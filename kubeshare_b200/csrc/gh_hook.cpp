@@ -351,17 +351,7 @@ void gh_host_sync_post(void) {
 void gh_register_exit_hook(void);
 static int read_quota_file_into_pool(gh_live* L) {
   if (!gh_cfg.quota_file[0]) return 0;
-  FILE* f = fopen(gh_cfg.quota_file, "r");
-  if (!f) return -1;
-  char* text = (char*)calloc(1, 1 << 16);
-  size_t n = fread(text, 1, (1 << 16) - 1, f);
-  fclose(f);
-  text[n] = 0;
-  int rc = 0;
-  // only (re)load rows this pool does not know yet: a reload resets adaptive quotas (scheduler.cpp:203-212)
-  if (gemhook_pool_find(L->pool, gh_cfg.pod_name) < 0) rc = gemhook_pool_load_config(L->pool, text, gh_cfg.swap_columns);
-  free(text);
-  return rc;
+  return gemhook_pool_sync_quota_file(L->pool, gh_cfg.quota_file, gh_cfg.swap_columns);
 }
 
 static void live_init(void) {
@@ -486,6 +476,7 @@ void gh_launch_slow(CUstream stream) {
       L->accumulated_token_ms += held < cap ? held : cap;
     }
     pthread_mutex_unlock(&L->mu);
+    if (L->pool) read_quota_file_into_pool(L);  // one stat() per token: pick up kubeshare-config's rewrites
     double quota = token_from_scheduler(L, overuse, next_burst);
     pthread_mutex_lock(&L->mu);
     if (!gh_cfg.dry_run) GH_CALL(cuEventRecord, L->ev_token, (CUstream)0);  // hook.cpp:543

@@ -257,6 +257,29 @@ GH_HOOK cuGraphLaunch_ptsz(CUgraphExec g, CUstream hStream) {
   launch_gate(hStream);
   return ((graphlaunch_fn)LATE(p_graphlaunch_pt, "cuGraphLaunch_ptsz"))(g, hStream);
 }
+// Virtual-memory-management allocations (PyTorch "expandable segments"): the physical handle is what consumes
+// device memory, so cuMemCreate is charged and cuMemRelease gives it back; mapping / address reservation is free.
+typedef CUresult(CUDAAPI* memcreate_fn)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+typedef CUresult(CUDAAPI* memrelease_fn)(CUmemGenericAllocationHandle);
+static void *p_memcreate, *p_memrelease;
+static inline uint64_t handle_key(CUmemGenericAllocationHandle h) { return (uint64_t)h ^ 0x8000000000000000ULL; }
+GH_HOOK cuMemCreate(CUmemGenericAllocationHandle* handle, size_t size, const CUmemAllocationProp* prop, unsigned long long flags) {
+  bool device = !prop || prop->location.type == CU_MEM_LOCATION_TYPE_DEVICE;
+  if (device && !gh_mem_reserve(size)) return CUDA_ERROR_OUT_OF_MEMORY;
+  CUresult r = ((memcreate_fn)LATE(p_memcreate, "cuMemCreate"))(handle, size, prop, flags);
+  if (!device) return r;
+  if (r != CUDA_SUCCESS) {
+    gh_mem_unreserve(size);
+    return r;
+  }
+  gh_mem_commit(handle_key(*handle), size);
+  return r;
+}
+GH_HOOK cuMemRelease(CUmemGenericAllocationHandle handle) {
+  gh_mem_free_key(handle_key(handle));
+  return ((memrelease_fn)LATE(p_memrelease, "cuMemRelease"))(handle);
+}
+
 static inline bool extra_syncs(void) { return gh_live_get() && gh_cfg.extra_hooks; }
 GH_HOOK cuStreamSynchronize(CUstream hStream) {
   bool x = extra_syncs();
@@ -317,6 +340,8 @@ static const HookEntry kHooks[] = {
     {"cuMemAllocFromPoolAsync", "cuMemAllocFromPoolAsync", (void*)&cuMemAllocFromPoolAsync, (void*)&cuMemAllocFromPoolAsync_ptsz},
     {"cuMemFreeAsync", "cuMemFreeAsync", (void*)&cuMemFreeAsync, (void*)&cuMemFreeAsync_ptsz},
     {"cuGraphLaunch", "cuGraphLaunch", (void*)&cuGraphLaunch, (void*)&cuGraphLaunch_ptsz},
+    {"cuMemCreate", "cuMemCreate", (void*)&cuMemCreate, nullptr},
+    {"cuMemRelease", "cuMemRelease", (void*)&cuMemRelease, nullptr},
     {"cuStreamSynchronize", "cuStreamSynchronize", (void*)&cuStreamSynchronize, (void*)&cuStreamSynchronize_ptsz},
     {"cuEventSynchronize", "cuEventSynchronize", (void*)&cuEventSynchronize, nullptr},
 };
@@ -328,7 +353,7 @@ static const char* const kHookedNames[] = {
     "cuArrayCreate_v2", "cuArray3DCreate_v2", "cuMipmappedArrayCreate", "cuArrayDestroy",
     "cuMipmappedArrayDestroy", "cuMemGetInfo_v2", "cuDeviceTotalMem_v2", "cuCtxSynchronize",
     "cuMemcpyAtoH_v2", "cuMemcpyDtoH_v2", "cuMemcpyHtoA_v2", "cuMemcpyHtoD_v2",
-    "cuMemAllocAsync", "cuMemAllocFromPoolAsync", "cuMemFreeAsync", "cuGraphLaunch", "cuStreamSynchronize",
+    "cuMemAllocAsync", "cuMemAllocFromPoolAsync", "cuMemFreeAsync", "cuGraphLaunch", "cuMemCreate", "cuMemRelease", "cuStreamSynchronize",
     "cuEventSynchronize", nullptr};
 
 extern "C" __attribute__((visibility("default"))) const char* const* gemhook_hooked_symbols(size_t* count) {

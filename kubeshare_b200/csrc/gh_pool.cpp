@@ -104,6 +104,7 @@ struct alignas(64) Header {
   uint64_t total_grants;
   uint32_t ledger_len;
   uint32_t ledger_dropped;
+  std::atomic<uint64_t> quota_stamp;  // mtime/size stamp of the quota file last loaded (gemhook_pool_sync_quota_file)
   uint64_t boot_id;  // CLOCK_MONOTONIC restarts at boot: a pool file that survived a reboot is re-initialised
 };
 
@@ -497,6 +498,28 @@ GH_EXPORT int gemhook_pool_load_config(gemhook_pool* p, const char* text, int sw
   }
   p->unlock();
   return loaded == n ? (int)n : -1;
+}
+
+// Keep the pool in step with the quota file kubeshare-config rewrites (what gem-schd does with inotify,
+// scheduler.cpp:219-265): cheap stat, reload only when the file's (mtime, size) stamp differs from the one recorded
+// in the pool -- so of N co-resident clients only the first to notice reloads.  1 = reloaded, 0 = unchanged, -1 = error.
+GH_EXPORT int gemhook_pool_sync_quota_file(gemhook_pool* p, const char* path, int swap_columns) {
+  if (!p || !path || !*path) return -1;
+  struct stat st;
+  if (stat(path, &st) != 0) return -1;
+  uint64_t stamp = ((uint64_t)st.st_mtim.tv_sec * 1000000000ULL + (uint64_t)st.st_mtim.tv_nsec) * 31ULL + (uint64_t)st.st_size + 1;
+  if (p->r->h.quota_stamp.load(std::memory_order_acquire) == stamp) return 0;
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  char* text = (char*)calloc(1, 1 << 16);
+  size_t n = fread(text, 1, (1 << 16) - 1, f);
+  fclose(f);
+  text[n] = 0;
+  int rc = gemhook_pool_load_config(p, text, swap_columns);
+  free(text);
+  if (rc < 0) return -1;  // half-written file: keep the old stamp, try again at the next renewal
+  p->r->h.quota_stamp.store(stamp, std::memory_order_release);
+  return 1;
 }
 
 GH_EXPORT int gemhook_pool_find(const gemhook_pool* p, const char* name) {

@@ -343,8 +343,25 @@ int main(int argc, char** argv) {
     CK(cuStreamSynchronize(st));
     size_t fr2 = 0;
     cuMemGetInfo(&fr2, &tot);
-    fprintf(out, "{\"mode\": \"modern\", \"rc\": [%d, %d, %d], \"free\": %zu, \"free_after\": %zu, \"total\": %zu}\n",
-            (int)r1, (int)r2, (int)r3, fr, fr2, tot);
+    /* virtual memory management: the physical handle is what is charged */
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = 0;
+    size_t gran = 0;
+    cuMemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM);
+    CUmemGenericAllocationHandle h1 = 0, h2 = 0;
+    CUresult v1 = cuMemCreate(&h1, gran ? gran : 4000, &prop, 0);
+    size_t fr3 = 0, fr4 = 0;
+    cuMemGetInfo(&fr3, &tot);
+    CUresult v2 = cuMemCreate(&h2, (gran ? gran : 4000) * 4096, &prop, 0);
+    if (v2 == CUDA_SUCCESS) cuMemRelease(h2);
+    if (v1 == CUDA_SUCCESS) cuMemRelease(h1);
+    cuMemGetInfo(&fr4, &tot);
+    fprintf(out, "{\"mode\": \"modern\", \"rc\": [%d, %d, %d], \"free\": %zu, \"free_after\": %zu, \"total\": %zu, "
+            "\"vmm\": {\"gran\": %zu, \"rc\": [%d, %d], \"free_held\": %zu, \"free_released\": %zu}}\n",
+            (int)r1, (int)r2, (int)r3, fr, fr2, tot, gran, (int)v1, (int)v2, fr3, fr4);
     if (r1 == CUDA_SUCCESS) cuMemFreeAsync(a, st);
     CK(cuStreamSynchronize(st));
   } else if (!strcmp(mode, "probe")) {

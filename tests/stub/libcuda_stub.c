@@ -260,3 +260,11 @@ CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { return CUDA_S
 CUresult cuMemAllocAsync(CUdeviceptr* p, size_t bytes, CUstream s) { return fake_alloc(p, bytes); }
 CUresult cuMemAllocFromPoolAsync(CUdeviceptr* p, size_t bytes, CUmemoryPool pool, CUstream s) { return fake_alloc(p, bytes); }
 CUresult cuMemFreeAsync(CUdeviceptr p, CUstream s) { return cuMemFree_v2(p); }
+CUresult cuMemGetAllocationGranularity(size_t* g, const CUmemAllocationProp* prop, CUmemAllocationGranularity_flags o) { *g = 1000; return CUDA_SUCCESS; }
+CUresult cuMemCreate(CUmemGenericAllocationHandle* h, size_t size, const CUmemAllocationProp* prop, unsigned long long flags) {
+  CUdeviceptr p;
+  CUresult r = fake_alloc(&p, size);
+  *h = (CUmemGenericAllocationHandle)p;
+  return r;
+}
+CUresult cuMemRelease(CUmemGenericAllocationHandle h) { return cuMemFree_v2((CUdeviceptr)h); }

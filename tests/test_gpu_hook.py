@@ -217,6 +217,14 @@ def test_modern_entry_points_on_real_driver():
     assert st["launches"] == 100 and res["rc"] == [0, 0, 2]
     assert (res["free"], res["free_after"], res["total"]) == (2000, 4000, 5000)
     assert st["slow_path"] >= 5 and st["gpu_ns"] == st["gpu_ns_host"]
+    # virtual memory management (PyTorch expandable segments): cuMemCreate is charged, cuMemRelease gives it back
+    cap = 64 << 20
+    with tempfile.TemporaryDirectory() as tmp:
+        res = storm(env_pool(tmp, quota="1\nbench/c0 1.0 1.0 %d\n" % cap), "--mode", "modern")
+    g = res["vmm"]["gran"]
+    assert g >= 4096 and res["vmm"]["rc"] == [0, 2]                 # one granule fits, 4096 granules do not
+    assert res["vmm"]["free_held"] == cap - 1000 - 3000 - g        # a (1000) and c (3000) are still allocated
+    assert res["vmm"]["free_released"] == cap - 1000 - 3000
 
 
 def test_pytorch_application_under_the_hook():

@@ -320,3 +320,35 @@ time.sleep(60)
         assert time.time() - t0 < 0.2
         L.gemhook_pool_detach(p)
         L.gemhook_pool_close(p)
+
+
+def test_quota_file_sync_reloads_only_on_change():
+    import tempfile
+    import time
+
+    L = kb.lib()
+    with tempfile.TemporaryDirectory() as tmp:
+        qf = os.path.join(tmp, "q.txt")
+        with open(qf, "w") as f:
+            f.write("1\nns/a 0.5 1.0 100\n")
+        p = L.gemhook_pool_open(os.path.join(tmp, "pool").encode(), 1, 300.0, 20.0, 10000.0, 0)
+        assert L.gemhook_pool_sync_quota_file(p, qf.encode(), 0) == 1
+        assert L.gemhook_pool_sync_quota_file(p, qf.encode(), 0) == 0      # unchanged: one stat, no reload
+        q2 = L.gemhook_pool_open(os.path.join(tmp, "pool").encode(), 0, 0, 0, 0, 0)
+        assert L.gemhook_pool_sync_quota_file(q2, qf.encode(), 0) == 0     # the stamp lives in the pool: peers see it
+        time.sleep(0.01)
+        with open(qf, "w") as f:
+            f.write("2\nns/a 0.5 1.0 777\nns/new 0.25 0.5 4242\n")
+        assert L.gemhook_pool_sync_quota_file(q2, qf.encode(), 0) == 1
+        assert L.gemhook_pool_sync_quota_file(p, qf.encode(), 0) == 0
+        u, lim = C.c_uint64(), C.c_uint64()
+        L.gemhook_pool_mem_info(p, L.gemhook_pool_find(p, b"ns/new"), C.byref(u), C.byref(lim))
+        assert lim.value == 4242
+        L.gemhook_pool_mem_info(p, 0, C.byref(u), C.byref(lim))
+        assert lim.value == 777
+        with open(qf, "w") as f:
+            f.write("3\nns/a 0.5 1.0 777\n")                              # half-written: count says 3, one row
+        assert L.gemhook_pool_sync_quota_file(p, qf.encode(), 0) == -1
+        assert L.gemhook_pool_sync_quota_file(p, b"/nonexistent/file", 0) == -1
+        L.gemhook_pool_close(q2)
+        L.gemhook_pool_close(p)
