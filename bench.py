@@ -484,4 +484,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception as e:  # noqa: BLE001
+        if "--impl" in sys.argv and "reference" in sys.argv and int(os.environ.get("RANK", "0")) == 0:
+            # contract: the reference arm never fails the driver; say why it could not run
+            print(json.dumps({"impl": "reference", "unavailable": "reference stack failed on this box: %r" % (e,)}))
+            sys.exit(0)
+        raise

@@ -7,8 +7,11 @@
 // the SAME pool that native hooks (GEMHOOK_POOL) arbitrate in.  Old and new hooks on one GPU therefore share one
 // ledger and one token.
 //
-//   gem-arbiter --pool FILE -p DIR -f QUOTAFILE [-P PORT]... [-q BASE] [-m MIN] [-w WINDOW] [--mirror FILE]
-//               [--columns limit_request] [-v]
+//   gem-arbiter --pool FILE -p DIR -f QUOTAFILE [-P PORT]... [--port-file FILE] [-q BASE] [-m MIN] [-w WINDOW]
+//               [--mirror FILE] [--columns limit_request] [-v]
+// --port-file is KubeShare's /kubeshare/scheduler/podmanagerport/<GPU-UUID> ("N" then "name port" rows,
+// pkg/config/query.go:57, 86-98): a listener is opened for every port listed and closed when the row disappears --
+// what launcher.py does by spawning / killing one gem-pmgr per row (reference launcher.py:34-67), without Python.
 // Flags -P -q -m -w -f -p mean what they mean to gem-schd (scheduler.cpp:555-604).  Several -P give several
 // listeners (KubeShare hands every pod its own POD_MANAGER_PORT, pkg/scheduler/node.go:14).
 //
@@ -161,6 +164,12 @@ static void* conn_main(void* arg) {
   return nullptr;
 }
 
+#include <map>
+static std::map<int, int> g_listeners;  // port -> listening fd (dynamic ones from --port-file)
+static pthread_mutex_t g_listeners_mu = PTHREAD_MUTEX_INITIALIZER;
+static std::string g_port_file;
+static std::vector<int> g_static_ports;  // from -P: never closed by the port file
+
 static void* listen_main(void* arg) {
   int port = (int)(intptr_t)arg;
   int ls = socket(AF_INET, SOCK_STREAM, 0);
@@ -176,12 +185,81 @@ static void* listen_main(void* arg) {
     exit(1);
   }
   fprintf(stderr, "[gem-arbiter] listening on port %d\n", port);
+  pthread_mutex_lock(&g_listeners_mu);
+  g_listeners[port] = ls;
+  pthread_mutex_unlock(&g_listeners_mu);
   for (;;) {
     int fd = accept(ls, nullptr, nullptr);
-    if (fd < 0) continue;
+    if (fd < 0) {
+      if (errno == EBADF || errno == EINVAL) break;  // listener closed: the pod left the port file
+      continue;
+    }
     pthread_t t;
     pthread_create(&t, nullptr, conn_main, (void*)(intptr_t)fd);
     pthread_detach(t);
+  }
+  fprintf(stderr, "[gem-arbiter] port %d closed\n", port);
+  return nullptr;
+}
+
+// podmanagerport/<UUID>: open listeners for new rows, close the ones that disappeared
+static void sync_port_file(void) {
+  std::string text;
+  if (g_port_file.empty() || !read_file(g_port_file, &text)) return;
+  std::vector<int> want;
+  const char* c = text.c_str();
+  char* end = nullptr;
+  long n = strtol(c, &end, 10);
+  c = end;
+  for (long i = 0; i < n; i++) {
+    char name[256];
+    int port = 0, used = 0;
+    if (sscanf(c, " %255s %d%n", name, &port, &used) != 2) break;
+    c += used;
+    if (port > 0) want.push_back(port);
+  }
+  std::vector<int> to_open, to_close;
+  pthread_mutex_lock(&g_listeners_mu);
+  for (int p : want)
+    if (!g_listeners.count(p)) to_open.push_back(p);
+  for (auto& kv : g_listeners) {
+    bool keep = false;
+    for (int p : g_static_ports) keep = keep || p == kv.first;
+    for (int p : want) keep = keep || p == kv.first;
+    if (!keep) to_close.push_back(kv.first);
+  }
+  for (int p : to_close) {
+    shutdown(g_listeners[p], SHUT_RDWR);
+    close(g_listeners[p]);
+    g_listeners.erase(p);
+  }
+  pthread_mutex_unlock(&g_listeners_mu);
+  for (int p : to_open) {
+    pthread_t t;
+    pthread_create(&t, nullptr, listen_main, (void*)(intptr_t)p);
+    pthread_detach(t);
+  }
+}
+
+static void* port_watch_main(void*) {
+  std::string dir = g_port_file, base = g_port_file;
+  size_t slash = g_port_file.find_last_of('/');
+  if (slash == std::string::npos) dir = ".";
+  else {
+    dir = g_port_file.substr(0, slash);
+    base = g_port_file.substr(slash + 1);
+  }
+  int fd = inotify_init();
+  if (fd < 0 || inotify_add_watch(fd, dir.c_str(), IN_CLOSE_WRITE | IN_MOVED_TO) < 0) return nullptr;
+  char buf[4096] __attribute__((aligned(8)));
+  for (;;) {
+    ssize_t len = read(fd, buf, sizeof(buf));
+    if (len <= 0) continue;
+    for (char* p = buf; p < buf + len;) {
+      struct inotify_event* ev = (struct inotify_event*)p;
+      if (ev->len && base == ev->name) sync_port_file();
+      p += sizeof(struct inotify_event) + ev->len;
+    }
   }
   return nullptr;
 }
@@ -201,6 +279,7 @@ int main(int argc, char** argv) {
     else if (a == "-m" || a == "--min_quota") min_q = atof(next());
     else if (a == "-w" || a == "--window") window = atof(next());
     else if (a == "--mirror") g_mirror = next();
+    else if (a == "--port-file") g_port_file = next();
     else if (a == "--columns") g_swap = !strcmp(next(), "limit_request");
     else if (a == "-v" || a == "--verbose") { g_verbose = 1; if (i + 1 < argc && argv[i + 1][0] != '-') i++; }
     else if (a == "-h" || a == "--help") {
@@ -212,7 +291,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "gem-arbiter: --pool FILE is required\n");
     return 2;
   }
-  if (ports.empty()) {
+  if (ports.empty() && g_port_file.empty()) {
     const char* e = getenv("POD_MANAGER_PORT");  // started in gem-pmgr's place: same env (pod-manager.cpp:180-184)
     ports.push_back(e ? atoi(e) : 50051);
   }
@@ -226,10 +305,16 @@ int main(int argc, char** argv) {
   pthread_t t;
   pthread_create(&t, nullptr, watch_main, nullptr);
   pthread_detach(t);
-  for (size_t i = 1; i < ports.size(); i++) {
+  g_static_ports = ports;
+  for (size_t i = 0; i < ports.size(); i++) {
     pthread_create(&t, nullptr, listen_main, (void*)(intptr_t)ports[i]);
     pthread_detach(t);
   }
-  listen_main((void*)(intptr_t)ports[0]);
+  if (!g_port_file.empty()) {
+    sync_port_file();
+    pthread_create(&t, nullptr, port_watch_main, nullptr);
+    pthread_detach(t);
+  }
+  for (;;) pause();
   return 0;
 }

@@ -154,3 +154,42 @@ def test_poolctl_usage_export():
         assert 'gemhook_mem_used_bytes{pod="ns/b",request="0.25",limit="1"} 1234' in prom
         assert 'gemhook_token_seconds_total{pod="ns/a"} 0.300000' in prom
         L.gemhook_pool_close(p)
+
+
+def test_port_file_listeners_follow_kubeshare_config():
+    """Launcher parity: podmanagerport/<UUID> rows appear -> listeners open; rows vanish -> they close."""
+    with tempfile.TemporaryDirectory() as tmp:
+        pf = os.path.join(tmp, "ports")
+        p1, p2 = wp.free_port(), wp.free_port()
+        with open(pf, "w") as f:
+            f.write("1\nns/a %d\n" % p1)
+        a = Arbiter(tmp, "2\nns/a 0.5 1.0 100\nns/b 0.5 1.0 200\n", extra=("--port-file", pf))
+        try:
+            time.sleep(0.3)
+            assert wp.Client("127.0.0.1", p1, "ns/a").mem_limit() == (0, 100)
+            with open(pf, "w") as f:
+                f.write("2\nns/a %d\nns/b %d\n" % (p1, p2))
+            deadline = time.time() + 5
+            ok = False
+            while time.time() < deadline and not ok:
+                try:
+                    ok = wp.Client("127.0.0.1", p2, "ns/b", timeout=1).mem_limit() == (0, 200)
+                except OSError:
+                    time.sleep(0.05)
+            assert ok
+            with open(pf, "w") as f:
+                f.write("1\nns/b %d\n" % p2)
+            deadline = time.time() + 5
+            closed = False
+            while time.time() < deadline and not closed:
+                try:
+                    c = wp.Client("127.0.0.1", p1, "ns/a", timeout=1)
+                    c.mem_limit()
+                    c.close()
+                    time.sleep(0.05)
+                except (OSError, ConnectionError):
+                    closed = True
+            assert closed
+            assert wp.Client("127.0.0.1", a.port, "ns/a").mem_limit() == (0, 100)   # the static -P listener stays
+        finally:
+            a.close()
