@@ -308,6 +308,31 @@ int main(int argc, char** argv) {
     free_gpa(c);
     cuMemFree(b);
     cuMemFree(a);
+  } else if (!strcmp(mode, "arrays")) {
+    /* pitch and array allocations: what is charged against gpu_mem (reference hook.cpp:629-680) */
+    size_t fr[6] = {0}, tot = 0, pitch = 0;
+    CUdeviceptr dp = 0;
+    CUarray a2 = NULL, a3 = NULL;
+    CUDA_ARRAY_DESCRIPTOR d2;
+    CUDA_ARRAY3D_DESCRIPTOR d3;
+    memset(&d2, 0, sizeof(d2));
+    memset(&d3, 0, sizeof(d3));
+    d2.Width = 16; d2.Height = 8; d2.NumChannels = 4; d2.Format = CU_AD_FORMAT_FLOAT;        /* 16*8*4*4 = 2048 B */
+    d3.Width = 8; d3.Height = 4; d3.Depth = 2; d3.NumChannels = 2; d3.Format = CU_AD_FORMAT_HALF; /* 8*4*2*2*2 = 256 B */
+    cuMemGetInfo(&fr[0], &tot);
+    CUresult r1 = cuMemAllocPitch(&dp, &pitch, 100, 7, 4);
+    cuMemGetInfo(&fr[1], &tot);
+    CUresult r2 = cuArrayCreate(&a2, &d2);
+    cuMemGetInfo(&fr[2], &tot);
+    CUresult r3 = cuArray3DCreate(&a3, &d3);
+    cuMemGetInfo(&fr[3], &tot);
+    if (r3 == CUDA_SUCCESS) cuArrayDestroy(a3);
+    if (r2 == CUDA_SUCCESS) cuArrayDestroy(a2);
+    cuMemGetInfo(&fr[4], &tot);
+    if (r1 == CUDA_SUCCESS) cuMemFree(dp);
+    cuMemGetInfo(&fr[5], &tot);
+    fprintf(out, "{\"mode\": \"arrays\", \"rc\": [%d, %d, %d], \"pitch\": %zu, \"free\": [%zu, %zu, %zu, %zu, %zu, %zu], \"total\": %zu}\n",
+            (int)r1, (int)r2, (int)r3, pitch, fr[0], fr[1], fr[2], fr[3], fr[4], fr[5], tot);
   } else if (!strcmp(mode, "mt")) {
     int T = nclients > 1 ? nclients : 4;  /* --nclients doubles as thread count here */
     pthread_t tid[64];

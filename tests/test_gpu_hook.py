@@ -146,15 +146,34 @@ def test_accumulated_gpu_ms_within_1pct_of_reference_ledger():
                 dumps = [d for d in dumps if os.path.basename(d)[0].isdigit()]
                 assert dumps, "gem-schd did not dump its ledger"
                 total_ms, n = _ledger_total(dumps[0], "bench/c0")
+                led = [e for e in json.load(open(dumps[0])) if e["container"] == "bench/c0"]
+                closed_ms = sum(e["end"] - e["start"] for e in led[:-1]) * 1e3
                 extra = stats(tmp)[0] if which == "ours" else {}
-                totals[which] = {"ledger_ms": total_ms, "tokens": n, "wall_ms": res["wall_s"] * 1e3, "stats": extra}
+                totals[which] = {"ledger_ms": total_ms, "closed_ms": closed_ms, "tokens": n, "wall_ms": res["wall_s"] * 1e3,
+                                 "stats": extra}
             finally:
                 pmgr.kill()
                 schd.kill()
                 pmgr.wait()
                 schd.wait()
+    # third arm: the same storm with the credit pool doing gem-pmgr's + gem-schd's job (no daemon at all)
+    with tempfile.TemporaryDirectory() as tmp:
+        res = storm(env_pool(tmp), "--mode", "storm", "--steps", 12, "--warmup", 2, "--step-launches", 65536)
+        L = kb.lib()
+        p = L.gemhook_pool_open(os.path.join(tmp, "pool").encode(), 0, 0, 0, 0, 0)
+        n = L.gemhook_pool_history(p, None, None, None, 0)
+        import ctypes as C
+        sl, a, b = (C.c_int * n)(), (C.c_double * n)(), (C.c_double * n)()
+        L.gemhook_pool_history(p, sl, a, b, n)
+        L.gemhook_pool_close(p)
+        spans = [(a[i], b[i]) for i in range(n)]
+        totals["pool"] = {"tokens": n, "closed_ms": sum(e - s for s, e in spans[:-1]), "wall_ms": res["wall_s"] * 1e3}
     ref, ours = totals["reference"], totals["ours"]
     print("ledger totals:", json.dumps(totals))
+    # closed tokens only (the last, still-held token is clipped at exit by the pool but kept at full quota by
+    # gem-schd): same number of tokens, same closed time within 1 %
+    assert totals["pool"]["tokens"] == ref["tokens"] == ours["tokens"]
+    assert abs(totals["pool"]["closed_ms"] - ref["closed_ms"]) <= 0.01 * ref["closed_ms"], totals
     # identical launch trace, identical policy, identical daemons: the ledgers agree within 1 %
     assert abs(ours["ledger_ms"] - ref["ledger_ms"]) <= 0.01 * ref["ledger_ms"], totals
     # and our own per-token view of the same quantity matches what gem-schd recorded for us (within 1 %)

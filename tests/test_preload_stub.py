@@ -323,3 +323,17 @@ def test_multithreaded_client_no_lost_launches_no_deadlock():
         assert stub["launches"] >= 160000          # + our own reduce launches
         assert st["mem_used"] == 0 and st["allocs_denied"] == 0
         assert st["token_requests"] >= 3
+
+
+def test_pitch_and_array_charges_follow_the_reference_byte_rules():
+    """hook.cpp:629-680: pitch allocations are charged pitch*height with the REAL pitch, arrays W*H*[D*]C*fmt."""
+    O = orc.load()
+    with tempfile.TemporaryDirectory() as tmp:
+        res = run_storm(hooked_env(tmp, quota="1\nbench/c0 1.0 1.0 5000\n"), "--mode", "arrays")
+    pitch_bytes = res["pitch"] * 7
+    a2 = O.orc_array_bytes(16, 8, 0, 4, 0x20, 0)
+    a3 = O.orc_array_bytes(8, 4, 2, 2, 0x10, 1)
+    assert (res["pitch"], pitch_bytes, a2, a3) == (512, 3584, 2048, 256)
+    # 3584 fits in 5000; +2048 does not (denied, the driver is never asked); +256 fits
+    assert res["rc"] == [0, 2, 0]
+    assert res["free"] == [5000, 5000 - 3584, 5000 - 3584, 5000 - 3584 - 256, 5000 - 3584, 5000] and res["total"] == 5000
