@@ -138,7 +138,7 @@ def test_accumulated_gpu_ms_within_1pct_of_reference_ledger():
                                GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"))
                 else:
                     env.update(LD_PRELOAD=os.path.join(REF, "libgemhook_ref.so.1"))
-                res = storm(env, "--mode", "storm", "--steps", 12, "--warmup", 2, "--step-launches", 65536)
+                res = storm(env, "--mode", "storm", "--steps", 30, "--warmup", 2, "--step-launches", 65536)
                 time.sleep(0.2)
                 schd.send_signal(signal.SIGINT)
                 schd.wait(timeout=20)
@@ -158,7 +158,7 @@ def test_accumulated_gpu_ms_within_1pct_of_reference_ledger():
                 schd.wait()
     # third arm: the same storm with the credit pool doing gem-pmgr's + gem-schd's job (no daemon at all)
     with tempfile.TemporaryDirectory() as tmp:
-        res = storm(env_pool(tmp), "--mode", "storm", "--steps", 12, "--warmup", 2, "--step-launches", 65536)
+        res = storm(env_pool(tmp), "--mode", "storm", "--steps", 30, "--warmup", 2, "--step-launches", 65536)
         L = kb.lib()
         p = L.gemhook_pool_open(os.path.join(tmp, "pool").encode(), 0, 0, 0, 0, 0)
         n = L.gemhook_pool_history(p, None, None, None, 0)
