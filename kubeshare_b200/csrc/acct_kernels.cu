@@ -61,12 +61,19 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
   return v;
 }
 
-// bins layout per warp: ns[nslots][32] u64 | la[nslots][32] u64 | rc[nslots][32] u32  (20 B per column cell)
-#define GEMHOOK_BIN_BYTES_PER_SLOT (32u * 20u)
+}  // extern "C" (templates below need C++ linkage)
+
+// Privatised bins, per warp: ns[nslots][COLS] u64 | la[nslots][COLS] u64 | rc[nslots][COLS] u32 (20 B per cell).
+// COLS = 32: every lane owns a column -> plain read-modify-write, no races, conflict-free banks.
+// COLS = 16: lanes L and L+16 share column L and take turns (two phases per tile separated by __syncwarp):
+//            half the shared memory per slot.  The host picks it for nslots > 16: with 32 columns the bins of 20+
+//            slots eat so much of the 228 KB L1/shared array that too few loads can be in flight (measured on B200:
+//            6.5 TB/s up to 16 slots, 5.4 at 20, 4.5 at 32, 2.5 at 64 with 32 columns).
+template <unsigned COLS>
 __device__ __forceinline__ void bin_add(unsigned long long* ns, unsigned long long* la, unsigned* rc,
-                                        unsigned nslots, unsigned lane, const uint4& r) {
+                                        unsigned nslots, unsigned col, const uint4& r) {
   if (r.x < nslots) {
-    unsigned idx = r.x * 32u + lane;
+    unsigned idx = r.x * COLS + col;
     ns[idx] += ((unsigned long long)r.w << 32) | r.z;
     la[idx] += r.y;
     rc[idx] += 1u;
@@ -75,28 +82,30 @@ __device__ __forceinline__ void bin_add(unsigned long long* ns, unsigned long lo
 
 // dev_totals: [nslots][3] u64 running totals + 1 u64 publish counter (device memory, persistent)
 // ticket:     u32 zero-initialised, self-resetting
-__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, GEMHOOK_MIN_BLOCKS)
-gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigned nslots,
-                    unsigned long long* __restrict__ dev_totals, unsigned* __restrict__ ticket,
-                    gemhook_totals_page* __restrict__ page) {
+template <unsigned COLS>
+__device__ __forceinline__ void acct_reduce_body(const uint4* __restrict__ rec, unsigned long long n, unsigned nslots,
+                                                 unsigned long long* __restrict__ dev_totals,
+                                                 unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const unsigned nwarps = blockDim.x >> 5;
-  const unsigned per_warp_bytes = nslots * GEMHOOK_BIN_BYTES_PER_SLOT;
+  const unsigned col = lane & (COLS - 1u);
+  const unsigned per_warp_bytes = nslots * COLS * 20u;
   unsigned long long* ns = reinterpret_cast<unsigned long long*>(smem + warp * per_warp_bytes);
-  unsigned long long* la = ns + nslots * 32u;
-  unsigned* rc = reinterpret_cast<unsigned*>(la + nslots * 32u);
+  unsigned long long* la = ns + nslots * COLS;
+  unsigned* rc = reinterpret_cast<unsigned*>(la + nslots * COLS);
 
-  for (unsigned s = 0; s < nslots; s++) {
-    ns[s * 32u + lane] = 0ull;
-    la[s * 32u + lane] = 0ull;
-    rc[s * 32u + lane] = 0u;
+  if (lane < COLS) {
+    for (unsigned s = 0; s < nslots; s++) {
+      ns[s * COLS + lane] = 0ull;
+      la[s * COLS + lane] = 0ull;
+      rc[s * COLS + lane] = 0u;
+    }
   }
   __syncwarp();
 
-  // the per-column record count is u32: a lane sees at most n / (32 * warps) records, far below 2^32
-  // (the host splits reductions larger than 2^36 records, csrc/acct.cpp).
+  // the per-column record count is u32: a column sees at most 2 n / (32 * warps) records, far below 2^32
   const unsigned long long warps_total = (unsigned long long)gridDim.x * nwarps;
   const unsigned long long gwarp = (unsigned long long)blockIdx.x * nwarps + warp;
   const unsigned long long tile = 32ull * GEMHOOK_UNROLL;  // records per warp-iteration
@@ -107,31 +116,51 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigne
     uint4 r[GEMHOOK_UNROLL];
 #pragma unroll
     for (int u = 0; u < GEMHOOK_UNROLL; u++) r[u] = ld_stream_16(rec + base + (unsigned)u * 32u + lane);
+    if (COLS == 32u) {
 #pragma unroll
-    for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add(ns, la, rc, nslots, lane, r[u]);
+      for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add<COLS>(ns, la, rc, nslots, col, r[u]);
+    } else {
+      if (lane < 16u) {
+#pragma unroll
+        for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add<COLS>(ns, la, rc, nslots, col, r[u]);
+      }
+      __syncwarp();
+      if (lane >= 16u) {
+#pragma unroll
+        for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add<COLS>(ns, la, rc, nslots, col, r[u]);
+      }
+      __syncwarp();
+    }
   }
   if (base < n) {  // ragged tail of this warp's last tile
 #pragma unroll 1
     for (int u = 0; u < GEMHOOK_UNROLL; u++) {
       unsigned long long i = base + (unsigned)u * 32u + lane;
-      if (i < n) {
-        uint4 r = ld_stream_16(rec + i);
-        bin_add(ns, la, rc, nslots, lane, r);
+      uint4 r = make_uint4(0xffffffffu, 0u, 0u, 0u);  // out-of-range slot: ignored
+      if (i < n) r = ld_stream_16(rec + i);
+      if (COLS == 32u) {
+        bin_add<COLS>(ns, la, rc, nslots, col, r);
+      } else {
+        if (lane < 16u) bin_add<COLS>(ns, la, rc, nslots, col, r);
+        __syncwarp();
+        if (lane >= 16u) bin_add<COLS>(ns, la, rc, nslots, col, r);
+        __syncwarp();
       }
     }
   }
   __syncwarp();
 
-  // fold the 32 columns of every slot with shuffles; lane 0 leaves the warp result in column 0
+  // fold the columns of every slot with shuffles; lane 0 leaves the warp result in cells 0..2 of the slot's ns row
   for (unsigned s = 0; s < nslots; s++) {
-    unsigned long long a = warp_sum_u64(ns[s * 32u + lane]);
-    unsigned long long l = warp_sum_u64(la[s * 32u + lane]);
-    unsigned long long k = warp_sum_u64((unsigned long long)rc[s * 32u + lane]);
+    const bool own = lane < COLS;
+    unsigned long long a = warp_sum_u64(own ? ns[s * COLS + lane] : 0ull);
+    unsigned long long l = warp_sum_u64(own ? la[s * COLS + lane] : 0ull);
+    unsigned long long k = warp_sum_u64(own ? (unsigned long long)rc[s * COLS + lane] : 0ull);
     __syncwarp();
     if (lane == 0) {
-      ns[s * 32u] = a;
-      ns[s * 32u + 1] = l;
-      ns[s * 32u + 2] = k;
+      ns[s * COLS] = a;
+      ns[s * COLS + 1] = l;
+      ns[s * COLS + 2] = k;
     }
   }
   __syncthreads();
@@ -142,7 +171,7 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigne
     unsigned long long acc = 0ull;
     for (unsigned w = 0; w < nwarps; w++) {
       const unsigned long long* wns = reinterpret_cast<const unsigned long long*>(smem + w * per_warp_bytes);
-      acc += wns[s * 32u + f];
+      acc += wns[s * COLS + f];
     }
     if (acc) atomicAdd(dev_totals + t, acc);
   }
@@ -180,6 +209,23 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigne
       *reinterpret_cast<volatile unsigned long long*>(&page->epoch) = e;
     }
   }
+}
+
+extern "C" {
+
+__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, GEMHOOK_MIN_BLOCKS)
+gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigned nslots,
+                    unsigned long long* __restrict__ dev_totals, unsigned* __restrict__ ticket,
+                    gemhook_totals_page* __restrict__ page) {
+  acct_reduce_body<32u>(rec, n, nslots, dev_totals, ticket, page);
+}
+
+// 16-column variant for nslots > 16 (see bin_add)
+__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, GEMHOOK_MIN_BLOCKS)
+gemhook_acct_reduce_c16(const uint4* __restrict__ rec, unsigned long long n, unsigned nslots,
+                        unsigned long long* __restrict__ dev_totals, unsigned* __restrict__ ticket,
+                        gemhook_totals_page* __restrict__ page) {
+  acct_reduce_body<16u>(rec, n, nslots, dev_totals, ticket, page);
 }
 
 // Device-side timestamp record: one thread appends {slot, launches, globaltimer} -- used by the

@@ -31,7 +31,7 @@ struct totals_page {  // mirrors gemhook_totals_page in acct_kernels.cu
   volatile uint64_t buf[2][GEMHOOK_MAX_SLOTS * 3];
 };
 
-const unsigned BIN_BYTES_PER_SLOT = 32u * 20u;  // GEMHOOK_BIN_BYTES_PER_SLOT
+const unsigned BIN_CELL_BYTES = 20u;  // u64 ns + u64 launches + u32 count per (slot, column)
 #ifndef GEMHOOK_UNROLL
 #define GEMHOOK_UNROLL 16
 #endif
@@ -64,7 +64,7 @@ struct gemhook_acct {
   totals_page* page = nullptr;
   size_t ring_cap = 0;
   uint32_t nslots = 0;
-  unsigned warps = 8, smem_bytes = 0, max_blocks = 0;
+  unsigned warps = 8, cols = 32, smem_bytes = 0, max_blocks = 0;
   int sm_count = 0;
   std::atomic<uint64_t> kernel_launches{0};
   pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
@@ -92,7 +92,26 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
     return -1;
   }
   CU_TRY(GH_CALL(cuModuleLoadData, &a->mod, (const void*)_binary_acct_kernels_cubin_start));
-  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, "gemhook_acct_reduce"));
+  // Launch shape by slot count, from the sweep in profiles/r01_acct_reduce_nslots_sweep.jsonl (N = 2^26, B200):
+  //   <= 16 slots: 32 bin columns (every lane owns one), 8 warps/block           6.5-6.7 TB/s
+  //   17-24      : 16 columns (two lanes share one, two phases), 4 warps/block   5.5 TB/s
+  //   25-40      : 32 columns, 2 warps/block, bins may use 208 KB of the SM      4.9 TB/s
+  //   > 40       : 16 columns, 2 warps/block, 208 KB                             3.3 TB/s
+  // (shared memory and L1 share one 228 KB array; large bin tables leave few L1 sectors for loads in flight, and
+  //  the two-phase update of the 16-column layout costs ~15 % by itself -- both measured)
+  unsigned cap_kb = 160;
+  a->cols = 32;
+  a->warps = 8;
+  if (nslots > 40) { a->cols = 16; a->warps = 2; cap_kb = 208; }
+  else if (nslots > 24) { a->cols = 32; a->warps = 2; cap_kb = 208; }
+  else if (nslots > 16) { a->cols = 16; a->warps = 4; cap_kb = 128; }
+  if (const char* e = getenv("GEMHOOK_ACCT_COLS")) a->cols = (unsigned)atoi(e) == 16u ? 16u : 32u;
+  if (const char* e = getenv("GEMHOOK_ACCT_WARPS")) {
+    unsigned w = (unsigned)atoi(e);
+    if (w == 1u || w == 2u || w == 4u || w == 8u) a->warps = w;
+  }
+  if (const char* e = getenv("GEMHOOK_ACCT_SMEM_CAP_KB")) cap_kb = (unsigned)atoi(e);
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, a->cols == 32u ? "gemhook_acct_reduce" : "gemhook_acct_reduce_c16"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_clear, a->mod, "gemhook_acct_clear"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_stamp, a->mod, "gemhook_stamp"));
   CU_TRY(GH_CALL(cuStreamCreate, &a->stream, CU_STREAM_NON_BLOCKING));
@@ -100,14 +119,19 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   CU_TRY(GH_CALL(cuEventCreate, &a->ev1, CU_EVENT_DEFAULT));
 
   a->nslots = nslots;
-  // privatised bins: warps x nslots x 640 B of shared memory per block; keep >= 2 blocks per SM when possible
-  a->warps = (8u * nslots * BIN_BYTES_PER_SLOT <= 100u * 1024u) ? 8u : 4u;
-  a->smem_bytes = a->warps * nslots * BIN_BYTES_PER_SLOT;
+  // privatised bins: warps x nslots x cols x 20 B of shared memory per block; resident blocks per SM are limited so
+  // that their bins stay under cap_kb
+  const unsigned per_warp = nslots * a->cols * BIN_CELL_BYTES;
+  const unsigned cap = cap_kb * 1024u;
+  while (a->warps > 1u && a->warps * per_warp > 220u * 1024u) a->warps /= 2u;
+  a->smem_bytes = a->warps * per_warp;
   if (a->smem_bytes > 48u * 1024u)
     CU_TRY(GH_CALL(cuFuncSetAttribute, a->f_reduce, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)a->smem_bytes));
   int per_sm = 0;
   CU_TRY(GH_CALL(cuOccupancyMaxActiveBlocksPerMultiprocessor, &per_sm, a->f_reduce, (int)(a->warps * 32u),
                  (size_t)a->smem_bytes));
+  if (per_sm < 1) per_sm = 1;
+  if ((unsigned)per_sm * a->smem_bytes > cap && a->smem_bytes) per_sm = (int)(cap / a->smem_bytes);
   if (per_sm < 1) per_sm = 1;
   a->max_blocks = (unsigned)(per_sm * a->sm_count);  // one full wave: a multiple of the SM count
 
@@ -124,8 +148,8 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   a->page = (totals_page*)hp;
   CU_TRY(GH_CALL(cuMemHostGetDevicePointer_v2, &a->d_page, hp, 0));
   CU_TRY(GH_CALL(cuStreamSynchronize, a->stream));
-  GH_INFO("acct: %d SMs, nslots %u, %u warps/block, %u B smem, wave %u blocks", a->sm_count, nslots, a->warps,
-          a->smem_bytes, a->max_blocks);
+  GH_INFO("acct: %d SMs, nslots %u, %u bin columns, %u warps/block, %u B smem, wave %u blocks", a->sm_count, nslots,
+          a->cols, a->warps, a->smem_bytes, a->max_blocks);
   return 0;
 }
 
