@@ -7,8 +7,7 @@
  *      its cudart) binds these exactly as it binds the reference's libgemhook.so.1 -- by symbol
  *      interposition under LD_PRELOAD, through the interposed dlsym(), or through the interposed
  *      cuGetProcAddress / cuGetProcAddress_v2.  Prototypes are the driver API's own (cuda.h); they are
- *      listed here with the reference line each one replaces.  (GEMHOOK_DECLARE_DRIVER_SYMBOLS pulls
- *      the prototypes in for C callers that already include <cuda.h>.)
+ *      listed here with the reference line each one replaces.
  *
  *  (2) The CONTROL / ACCOUNTING API (gemhook_*): what a node agent, a test, or a Go/cgo binding calls:
  *      wire codec, launch-gate state machine with an injected clock, gpu_mem cap, shared credit pool,
@@ -54,8 +53,10 @@ extern "C" {
  *   cuMemcpyAtoH_v2 / cuMemcpyDtoH_v2 / cuMemcpyHtoA_v2 / cuMemcpyHtoD_v2
  *                                  hook.cpp:1005-1017  post: host_sync_call (701-722)
  *      (the reference exports cuMemcpyDtoH C++-mangled by accident, hook.cpp:925-926; we export it.)
- *   Extras behind GEMHOOK_EXTRA_HOOKS=1: cuLaunchKernelEx, cuStreamSynchronize,
- *   cuEventSynchronize, cuMemAllocAsync / cuMemFreeAsync, *_ptsz / *_ptds variants.
+ *   Beyond the reference: cuLaunchKernelEx and cuGraphLaunch pass the token gate;
+ *   cuMemAllocAsync / cuMemAllocFromPoolAsync / cuMemFreeAsync and cuMemCreate / cuMemRelease are charged against
+ *   gpu_mem; every stream-taking hook has its _ptsz / _ptds twin; cuStreamSynchronize / cuEventSynchronize are
+ *   exported and count as burst edges only with GEMHOOK_EXTRA_HOOKS=1.
  */
 const char *const *gemhook_hooked_symbols(size_t *count); /* names above, NULL-terminated */
 
