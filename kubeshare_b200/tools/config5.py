@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (reuses free_ports / pin / paths)
 
 FRACS = [0.1, 0.1, 0.4, 0.4]  # priority 0, 0, 100, 100
+WORK = ["--mode", "mnist"]    # overridden by --config 3 (bursty spin-kernel trace, 4 x min-fraction 0.25)
 
 
 def quota_text():
@@ -61,7 +62,7 @@ def run_device(gpu, impl, iters, core_base):
                      POD_NAME="bench/c%d" % i, GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json" % i))
         elif impl == "reference":
             e.update(LD_PRELOAD=os.path.join(bench.REFDIR, "libgemhook_ref.so.1"), POD_NAME="bench/c%d" % i, POD_MANAGER_PORT=str(ports[i]))
-        procs.append(sp.Popen([bench.STORM, "--mode", "mnist", "--iters", str(iters), "--client-id", str(i), "--nclients", str(len(FRACS)),
+        procs.append(sp.Popen([bench.STORM, *WORK, "--iters", str(iters), "--rounds", str(iters), "--client-id", str(i), "--nclients", str(len(FRACS)),
                                "--barrier-dir", tmp, "--out", os.path.join(tmp, "out.%d.json" % i)], env=e, stderr=sp.PIPE,
                               preexec_fn=bench.pin(core_base + i)))
     return tmp, daemons, procs
@@ -95,10 +96,19 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--impl", default="both", choices=["ours", "reference", "both", "unhooked"])
+    ap.add_argument("--config", type=int, default=5, choices=[3, 5],
+                    help="5: MNIST-shaped conv, fractions 0.1/0.1/0.4/0.4; 3: bursty trace (--iters = rounds), 4 x 0.25")
     args = ap.parse_args()
+    global FRACS, WORK
+    if args.config == 3:
+        FRACS, WORK = [0.25] * 4, ["--mode", "bursty"]
     sp.check_call([sys.executable, os.path.join(ROOT, "__graft_entry__.py")], stdout=sys.stderr)
-    out = {"config": "configs[4]: %d x B200, 4 clients/device, min-fractions %s, limit 1.0, mnist-shaped conv, %d iterations x 100 launches + DtoH"
-                     % (args.gpus, FRACS, args.iters)}
+    if args.config == 3:
+        out = {"config": "configs[2]: %d x B200, 4 clients, gpu_request 0.25 / gpu_limit 1.0, bursty trace seed 0xB200: %d rounds of "
+                         "{U{16..4096} launches of a ~5 us spin kernel; sync; sleep Exp(2 ms)}" % (args.gpus, args.iters)}
+    else:
+        out = {"config": "configs[4]: %d x B200, 4 clients/device, min-fractions %s, limit 1.0, mnist-shaped conv, %d iterations x 100 launches + DtoH"
+                         % (args.gpus, FRACS, args.iters)}
     impls = ["unhooked", "ours", "reference"] if args.impl == "both" else [args.impl]
     ncpu = len(bench.physical_cores())
     for impl in impls:
@@ -116,7 +126,8 @@ def main():
             else:
                 delivered = [r["wall_s"] for r in res]
             norm = [d / f for d, f in zip(delivered, FRACS)]
-            per_dev.append({"gpu": g, "launches": launches, "span_s": span, "launches_per_s": launches / span,
+            tok = [{k: s_.get(k) for k in ("token_requests", "slow_path", "token_wait_ms", "segments")} for s_ in stats]
+            per_dev.append({"gpu": g, "launches": launches, "span_s": span, "launches_per_s": launches / span, "hook": tok,
                             "client_wall_s": [r["wall_s"] for r in res], "delivered_s": delivered,
                             "jain_delivered_over_entitled": jain(norm), "jain_completion_time": jain([1.0 / r["wall_s"] for r in res])})
         out[impl] = {"aggregate_launches_per_s": sum(d["launches"] for d in per_dev) / max(d["span_s"] for d in per_dev),
