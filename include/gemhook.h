@@ -110,6 +110,8 @@ int gemhook_gate_tracker_complete(const gemhook_gate *);
 double gemhook_gate_quota_ms(const gemhook_gate *);
 double gemhook_gate_overuse_ms(const gemhook_gate *);
 int gemhook_gate_is_open(const gemhook_gate *); /* fast-path word: burst ongoing */
+/* give the current token up: the next launch renews (used by GEMHOOK_YIELD_ON_IDLE). */
+void gemhook_gate_expire(gemhook_gate *);
 double gemhook_estimate_full_burst(double measured_burst_ms, double measured_window_ms);
 
 /* stand-alone predictor (predictor.h:42-65) */
@@ -158,6 +160,8 @@ double gemhook_pool_accumulated_ms(const gemhook_pool *, int slot);
 double gemhook_pool_acquire(gemhook_pool *, int slot, double overuse_ms, double burst_ms);
 /* hand an outstanding token back early (client exit); the next waiter is scheduled immediately. */
 void gemhook_pool_release(gemhook_pool *, int slot);
+/* 1 if another client is waiting for the token (lock-free peek). */
+int gemhook_pool_others_waiting(const gemhook_pool *, int slot);
 /* declare the outstanding token timed out (scheduler.cpp:507-510) without touching the ledger. */
 void gemhook_pool_expire_token(gemhook_pool *);
 

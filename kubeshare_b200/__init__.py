@@ -74,7 +74,7 @@ def lib():
         "gemhook_gate_tracker_fire": (None, [vp, i64, C.c_float]),
         "gemhook_gate_tracker_complete": (C.c_int, [vp]),
         "gemhook_gate_quota_ms": (d, [vp]), "gemhook_gate_overuse_ms": (d, [vp]),
-        "gemhook_gate_is_open": (C.c_int, [vp]),
+        "gemhook_gate_is_open": (C.c_int, [vp]), "gemhook_gate_expire": (None, [vp]),
         "gemhook_estimate_full_burst": (d, [d, d]),
         "gemhook_predictor_new": (vp, [d]), "gemhook_predictor_free": (None, [vp]),
         "gemhook_predictor_record_start": (None, [vp, i64]), "gemhook_predictor_record_stop": (None, [vp, i64]),
@@ -92,7 +92,7 @@ def lib():
         "gemhook_pool_accumulated_ms": (d, [vp, C.c_int]),
         "gemhook_pool_acquire": (d, [vp, C.c_int, d, d]),
         "gemhook_pool_release": (None, [vp, C.c_int]),
-        "gemhook_pool_expire_token": (None, [vp]),
+        "gemhook_pool_expire_token": (None, [vp]), "gemhook_pool_others_waiting": (C.c_int, [vp, C.c_int]),
         "gemhook_pool_slot_info": (C.c_int, [vp, C.c_int, C.POINTER(SlotInfo)]),
         "gemhook_pool_attach": (C.c_int, [vp, C.c_int]), "gemhook_pool_detach": (None, [vp]),
         "gemhook_pool_reap": (C.c_int, [vp]),

@@ -146,4 +146,5 @@ void gh_config_load(void) {
   c.min_quota_ms = env_f("GEMHOOK_MIN_QUOTA_MS", 20.0);
   c.window_ms = env_f("GEMHOOK_WINDOW_MS", 10000.0);
   c.disabled = (int)env_i("GEMHOOK_DISABLE", 0);
+  c.yield_on_idle = (int)env_i("GEMHOOK_YIELD_ON_IDLE", 0);
 }

@@ -189,3 +189,4 @@ GH_EXPORT int gemhook_gate_tracker_complete(const gemhook_gate* g) { return g->t
 GH_EXPORT double gemhook_gate_quota_ms(const gemhook_gate* g) { return g->quota_ms; }
 GH_EXPORT double gemhook_gate_overuse_ms(const gemhook_gate* g) { return g->overuse_ms; }
 GH_EXPORT int gemhook_gate_is_open(const gemhook_gate* g) { return g->burst.open() ? 1 : 0; }
+GH_EXPORT void gemhook_gate_expire(gemhook_gate* g) { g->quota_ms = 0.0; }

@@ -41,6 +41,7 @@ struct gh_live {
   pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;  // guards gate + segments (expiration_status_mutex's role)
   pthread_cond_t renew_cv = PTHREAD_COND_INITIALIZER;
   bool renewing = false;
+  bool yielded = false;  // the running token was handed back at a sync (GEMHOOK_YIELD_ON_IDLE): its drain reports no overuse
   gemhook_gate* gate = nullptr;
   bool enabled = false;
   std::atomic<bool> cuda_ready{false};
@@ -90,7 +91,7 @@ struct gh_live {
   int stage_cur = 0;
 
   // stats
-  std::atomic<uint64_t> slow_path{0}, token_requests{0}, host_syncs{0}, segments{0};
+  std::atomic<uint64_t> slow_path{0}, token_requests{0}, host_syncs{0}, segments{0}, yields{0};
   uint64_t gpu_ns_host = 0;  // host-side running sum of the same records (cross-check of the device totals)
   std::atomic<uint64_t> token_wait_ns{0};
   double accumulated_token_ms = 0;
@@ -167,7 +168,10 @@ static void* tracker_main(void* arg) {
     pthread_mutex_lock(&L->mu);
     int64_t now = gh_now_ns();
     host_sync_locked(L, now);  // burst ends here; next launch re-evaluates the token
-    gemhook_gate_tracker_fire(L->gate, now, gh_cfg.dry_run ? (float)((double)(now - L->last_token_ns) / 1e6) : elapsed_ms);
+    if (L->yielded) elapsed_ms = 0.f;  // token given back early: nothing was overused
+    else if (gh_cfg.dry_run) elapsed_ms = (float)((double)(now - L->last_token_ns) / 1e6);
+    L->yielded = false;
+    gemhook_gate_tracker_fire(L->gate, now, elapsed_ms);
     if (L->cuda_ready && !gh_cfg.dry_run) resolve_pending_locked(L, false);
     pthread_mutex_unlock(&L->mu);
 
@@ -344,7 +348,27 @@ void gh_host_sync_post(void) {
   L->host_syncs.fetch_add(1, std::memory_order_relaxed);
   pthread_mutex_lock(&L->mu);
   host_sync_locked(L, gh_now_ns());  // nothing else here: the GPU is idle until the next launch arrives
+  bool yield = false;
+  if (gh_cfg.yield_on_idle && L->pool && !L->renewing && gemhook_gate_quota_ms(L->gate) > 0 &&
+      gemhook_pool_others_waiting(L->pool, L->slot)) {
+    // Work-conserving option (off by default: the reference keeps an idle token until it expires,
+    // scheduler.cpp:501-521).  The GPU is drained right now, somebody else wants it, and we do not know when our
+    // next burst comes: hand the token back; our next launch asks again like any returning client.
+    gemhook_gate_expire(L->gate);
+    L->yielded = true;
+    yield = true;
+    L->yields.fetch_add(1, std::memory_order_relaxed);
+  }
   pthread_mutex_unlock(&L->mu);
+  if (yield) {
+    gemhook_pool_release(L->pool, L->slot);
+    pthread_mutex_lock(&L->trk_mu);  // let the tracker finish the token it was timing (no GPU work pending)
+    if (!L->trk_done) {
+      L->trk_intr = true;
+      pthread_cond_signal(&L->trk_intr_cv);
+    }
+    pthread_mutex_unlock(&L->trk_mu);
+  }
 }
 
 // ---- initialisation -----------------------------------------------------------------------------------
@@ -573,12 +597,13 @@ static void write_stats_file(void) {
           "{\"pod\": \"%s\", \"pid\": %d, \"launches\": %llu, \"fast_path\": %llu, \"slow_path\": %llu, "
           "\"token_requests\": %llu, \"host_syncs\": %llu, \"segments\": %llu, \"acct_kernels\": %llu, "
           "\"gpu_ns\": %llu, \"gpu_ns_host\": %llu, \"mem_used\": %llu, \"mem_limit\": %llu, \"allocs_denied\": %llu, "
-          "\"quota_ms\": %.6f, \"overuse_ms\": %.6f, \"token_wait_ms\": %.6f, \"accumulated_token_ms\": %.6f}\n",
+          "\"quota_ms\": %.6f, \"overuse_ms\": %.6f, \"token_wait_ms\": %.6f, \"accumulated_token_ms\": %.6f, \"yields\": %llu}\n",
           gh_cfg.pod_name, (int)getpid(), (unsigned long long)s.launches, (unsigned long long)s.fast_path,
           (unsigned long long)s.slow_path, (unsigned long long)s.token_requests, (unsigned long long)s.host_syncs,
           (unsigned long long)s.segments, (unsigned long long)s.acct_kernels, (unsigned long long)s.gpu_ns,
           (unsigned long long)L->gpu_ns_host, (unsigned long long)s.mem_used, (unsigned long long)s.mem_limit,
-          (unsigned long long)gh_mem_denied(), s.quota_ms, s.overuse_ms, s.token_wait_ms, s.accumulated_token_ms);
+          (unsigned long long)gh_mem_denied(), s.quota_ms, s.overuse_ms, s.token_wait_ms, s.accumulated_token_ms,
+          (unsigned long long)L->yields.load());
   fclose(f);
 }
 

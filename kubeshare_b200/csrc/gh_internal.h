@@ -104,6 +104,7 @@ struct gh_config {
   uint32_t flush_records;
   double base_quota_ms, min_quota_ms, window_ms;
   int disabled;
+  int yield_on_idle;      // hand the token back at a host sync when another client is waiting (work-conserving option)
 };
 extern gh_config gh_cfg;
 void gh_config_load(void);

@@ -760,6 +760,7 @@ GH_EXPORT void gemhook_pool_release(gemhook_pool* p, int slot) {
       }
     Slot& s = p->r->slots[slot];
     if (s.grants) s.last_end = std::min(now, s.last_end);
+    s.pod_quota = 0.0;  // the pod-level token is gone with it: the next request must be forwarded
     h.holder = -1;
     double q, sl;
     p->schedule_locked(now, &who, &q, &sl);
@@ -777,6 +778,14 @@ GH_EXPORT void gemhook_pool_expire_token(gemhook_pool* p) {
   p->lock();
   p->r->h.holder = -1;
   p->unlock();
+}
+
+// 1 if some OTHER client is waiting for the token right now (lock-free peek, used by the yield-on-idle option)
+GH_EXPORT int gemhook_pool_others_waiting(const gemhook_pool* p, int slot) {
+  uint32_t n = p->r->h.nslots.load(std::memory_order_acquire);
+  for (uint32_t i = 0; i < n; i++)
+    if ((int)i != slot && p->r->slots[i].state.load(std::memory_order_relaxed) == ST_WAITING) return 1;
+  return 0;
 }
 
 // ---- gpu_mem cap: integer exact, requested bytes (hook.cpp:590-617, pod-manager.cpp:295-313) -----------

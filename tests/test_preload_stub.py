@@ -337,3 +337,28 @@ def test_pitch_and_array_charges_follow_the_reference_byte_rules():
     # 3584 fits in 5000; +2048 does not (denied, the driver is never asked); +256 fits
     assert res["rc"] == [0, 2, 0]
     assert res["free"] == [5000, 5000 - 3584, 5000 - 3584, 5000 - 3584 - 256, 5000 - 3584, 5000] and res["total"] == 5000
+
+
+def test_yield_on_idle_hands_the_token_over_at_syncs():
+    """Work-conserving option: with GEMHOOK_YIELD_ON_IDLE=1 a client that reaches a sync while another one waits
+    returns the token instead of sitting on it until the quota expires (reference behaviour, default)."""
+    results = {}
+    for y in (0, 1):
+        with tempfile.TemporaryDirectory() as tmp:
+            quota = "2\nbench/c0 0.5 1.0 %d\nbench/c1 0.5 1.0 %d\n" % (GIB8, GIB8)
+            procs = []
+            for i in range(2):
+                env = hooked_env(tmp, pod="bench/c%d" % i, quota=quota, GEMHOOK_YIELD_ON_IDLE=y, GEMHOOK_BASE_QUOTA_MS=200,
+                                 GEMHOOK_MIN_QUOTA_MS=200, STUB_REPORT=os.path.join(tmp, "stub%d.json" % i))
+                procs.append(sp.Popen([kb.STORM_PATH, "--mode", "bursty", "--rounds", "40", "--sleep-mean-ms", "3", "--client-id", str(i),
+                                       "--nclients", "2", "--barrier-dir", tmp, "--out", os.path.join(tmp, "out%d.json" % i)],
+                                      env=env, stderr=sp.PIPE))
+            for p in procs:
+                _, err = p.communicate(timeout=180)
+                assert p.returncode == 0, err.decode()[-1000:]
+            st = stats_files(tmp)
+            wall = max(json.load(open(os.path.join(tmp, "out%d.json" % i)))["wall_s"] for i in range(2))
+            results[y] = (wall, sum(s["yields"] for s in st), sum(s["token_requests"] for s in st))
+    assert results[0][1] == 0 and results[1][1] >= 10          # tokens really changed hands at sync points
+    assert results[1][2] > results[0][2]                         # ... which costs more (cheap) renewals
+    assert results[1][0] < results[0][0] * 1.05                  # and never makes the pair slower
