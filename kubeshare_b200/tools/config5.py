@@ -57,7 +57,9 @@ def run_device(gpu, impl, iters, core_base):
         time.sleep(0.4)
     for i in range(len(FRACS)):
         e = dict(env0)
-        if impl == "ours":
+        if impl in ("ours", "ours-yield"):
+            if impl == "ours-yield":
+                e["GEMHOOK_YIELD_ON_IDLE"] = "1"
             e.update(LD_PRELOAD=bench.HOOK, GEMHOOK_POOL=os.path.join(tmp, "pool"), GEMHOOK_QUOTA_FILE=os.path.join(tmp, "quota.txt"),
                      POD_NAME="bench/c%d" % i, GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json" % i))
         elif impl == "reference":
@@ -76,7 +78,7 @@ def collect(tmp, daemons, procs, impl):
                 raise RuntimeError("client failed: %s" % (err or b"").decode()[-400:])
         res = [json.load(open(os.path.join(tmp, "out.%d.json" % i))) for i in range(len(FRACS))]
         stats = []
-        if impl == "ours":
+        if impl in ("ours", "ours-yield"):
             stats = [json.load(open(os.path.join(tmp, "stats.%d.json" % i))) for i in range(len(FRACS))]
         return res, stats
     finally:
@@ -95,7 +97,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--iters", type=int, default=40)
-    ap.add_argument("--impl", default="both", choices=["ours", "reference", "both", "unhooked"])
+    ap.add_argument("--impl", default="both", choices=["ours", "ours-yield", "reference", "both", "unhooked"])
     ap.add_argument("--config", type=int, default=5, choices=[3, 5],
                     help="5: MNIST-shaped conv, fractions 0.1/0.1/0.4/0.4; 3: bursty trace (--iters = rounds), 4 x 0.25")
     args = ap.parse_args()
@@ -109,7 +111,7 @@ def main():
     else:
         out = {"config": "configs[4]: %d x B200, 4 clients/device, min-fractions %s, limit 1.0, mnist-shaped conv, %d iterations x 100 launches + DtoH"
                          % (args.gpus, FRACS, args.iters)}
-    impls = ["unhooked", "ours", "reference"] if args.impl == "both" else [args.impl]
+    impls = ["unhooked", "ours", "ours-yield", "reference"] if args.impl == "both" else [args.impl]
     ncpu = len(bench.physical_cores())
     for impl in impls:
         if impl == "reference" and not os.path.exists(os.path.join(bench.REFDIR, "libgemhook_ref.so.1")):
