@@ -112,6 +112,8 @@ double gemhook_gate_overuse_ms(const gemhook_gate *);
 int gemhook_gate_is_open(const gemhook_gate *); /* fast-path word: burst ongoing */
 /* give the current token up: the next launch renews (used by GEMHOOK_YIELD_ON_IDLE). */
 void gemhook_gate_expire(gemhook_gate *);
+/* largest idle window (sync -> next launch) seen in the last 3 s (window predictor, hook.cpp:178). */
+double gemhook_gate_predicted_window_ms(gemhook_gate *, int64_t now_ns);
 double gemhook_estimate_full_burst(double measured_burst_ms, double measured_window_ms);
 
 /* stand-alone predictor (predictor.h:42-65) */

@@ -75,6 +75,7 @@ def lib():
         "gemhook_gate_tracker_complete": (C.c_int, [vp]),
         "gemhook_gate_quota_ms": (d, [vp]), "gemhook_gate_overuse_ms": (d, [vp]),
         "gemhook_gate_is_open": (C.c_int, [vp]), "gemhook_gate_expire": (None, [vp]),
+        "gemhook_gate_predicted_window_ms": (d, [vp, i64]),
         "gemhook_estimate_full_burst": (d, [d, d]),
         "gemhook_predictor_new": (vp, [d]), "gemhook_predictor_free": (None, [vp]),
         "gemhook_predictor_record_start": (None, [vp, i64]), "gemhook_predictor_record_stop": (None, [vp, i64]),

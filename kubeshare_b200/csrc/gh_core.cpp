@@ -147,4 +147,5 @@ void gh_config_load(void) {
   c.window_ms = env_f("GEMHOOK_WINDOW_MS", 10000.0);
   c.disabled = (int)env_i("GEMHOOK_DISABLE", 0);
   c.yield_on_idle = (int)env_i("GEMHOOK_YIELD_ON_IDLE", 0);
+  c.yield_min_idle_ms = env_f("GEMHOOK_YIELD_MIN_IDLE_MS", 0.5);
 }

@@ -190,3 +190,4 @@ GH_EXPORT double gemhook_gate_quota_ms(const gemhook_gate* g) { return g->quota_
 GH_EXPORT double gemhook_gate_overuse_ms(const gemhook_gate* g) { return g->overuse_ms; }
 GH_EXPORT int gemhook_gate_is_open(const gemhook_gate* g) { return g->burst.open() ? 1 : 0; }
 GH_EXPORT void gemhook_gate_expire(gemhook_gate* g) { g->quota_ms = 0.0; }
+GH_EXPORT double gemhook_gate_predicted_window_ms(gemhook_gate* g, int64_t now_ns) { return g->window.predict_merged(now_ns); }

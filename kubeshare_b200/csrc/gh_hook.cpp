@@ -350,10 +350,13 @@ void gh_host_sync_post(void) {
   host_sync_locked(L, gh_now_ns());  // nothing else here: the GPU is idle until the next launch arrives
   bool yield = false;
   if (gh_cfg.yield_on_idle && L->pool && !L->renewing && gemhook_gate_quota_ms(L->gate) > 0 &&
-      gemhook_pool_others_waiting(L->pool, L->slot)) {
+      gemhook_pool_others_waiting(L->pool, L->slot) &&
+      gemhook_gate_predicted_window_ms(L->gate, gh_now_ns()) >= gh_cfg.yield_min_idle_ms) {
     // Work-conserving option (off by default: the reference keeps an idle token until it expires,
     // scheduler.cpp:501-521).  The GPU is drained right now, somebody else wants it, and we do not know when our
-    // next burst comes: hand the token back; our next launch asks again like any returning client.
+    // next burst comes -- but recent idle windows were long enough to pay for a hand-over (a launch storm that
+    // syncs every few ms and relaunches at once keeps its token): hand it back; our next launch asks again like
+    // any returning client.
     gemhook_gate_expire(L->gate);
     L->yielded = true;
     yield = true;

@@ -104,6 +104,7 @@ struct gh_config {
   uint32_t flush_records;
   double base_quota_ms, min_quota_ms, window_ms;
   int disabled;
+  double yield_min_idle_ms;  // ... only when the window predictor expects at least this much idle time
   int yield_on_idle;      // hand the token back at a host sync when another client is waiting (work-conserving option)
 };
 extern gh_config gh_cfg;
