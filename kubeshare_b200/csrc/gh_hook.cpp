@@ -41,6 +41,8 @@ struct gh_live {
   pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;  // guards gate + segments (expiration_status_mutex's role)
   pthread_cond_t renew_cv = PTHREAD_COND_INITIALIZER;
   bool renewing = false;
+  int64_t last_sync_ns = 0;     // when the last synchronising call returned
+  double last_window_ms = 0.0;  // idle gap between that return and the next launch (most recent one)
   bool yielded = false;  // the running token was handed back at a sync (GEMHOOK_YIELD_ON_IDLE): its drain reports no overuse
   gemhook_gate* gate = nullptr;
   bool enabled = false;
@@ -347,16 +349,16 @@ void gh_host_sync_post(void) {
   if (!L || !L->enabled) return;
   L->host_syncs.fetch_add(1, std::memory_order_relaxed);
   pthread_mutex_lock(&L->mu);
-  host_sync_locked(L, gh_now_ns());  // nothing else here: the GPU is idle until the next launch arrives
+  L->last_sync_ns = gh_now_ns();
+  host_sync_locked(L, L->last_sync_ns);  // nothing else here: the GPU is idle until the next launch arrives
   bool yield = false;
   if (gh_cfg.yield_on_idle && L->pool && !L->renewing && gemhook_gate_quota_ms(L->gate) > 0 &&
-      gemhook_pool_others_waiting(L->pool, L->slot) &&
-      gemhook_gate_predicted_window_ms(L->gate, gh_now_ns()) >= gh_cfg.yield_min_idle_ms) {
+      gemhook_pool_others_waiting(L->pool, L->slot) && L->last_window_ms >= gh_cfg.yield_min_idle_ms) {
     // Work-conserving option (off by default: the reference keeps an idle token until it expires,
     // scheduler.cpp:501-521).  The GPU is drained right now, somebody else wants it, and we do not know when our
-    // next burst comes -- but recent idle windows were long enough to pay for a hand-over (a launch storm that
-    // syncs every few ms and relaunches at once keeps its token): hand it back; our next launch asks again like
-    // any returning client.
+    // next burst comes -- but its last idle gap (sync -> next launch) was long enough to pay for a hand-over (a
+    // launch storm that relaunches right after every sync keeps its token): hand it back; our next launch asks
+    // again like any returning client.
     gemhook_gate_expire(L->gate);
     L->yielded = true;
     yield = true;
@@ -488,6 +490,10 @@ void gh_launch_slow(CUstream stream) {
   cuda_init_locked(L);
   while (L->renewing) pthread_cond_wait(&L->renew_cv, &L->mu);
   int64_t now = gh_now_ns();
+  if (L->last_sync_ns) {  // the application's most recent idle gap: decides whether yielding at syncs pays off
+    L->last_window_ms = (double)(now - L->last_sync_ns) / 1e6;
+    L->last_sync_ns = 0;
+  }
   if (L->enabled && gemhook_gate_launch_begin(L->gate, now)) {
     L->renewing = true;
     pthread_mutex_unlock(&L->mu);
