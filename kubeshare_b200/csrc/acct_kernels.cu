@@ -228,9 +228,10 @@ gemhook_acct_reduce_c16(const uint4* __restrict__ rec, unsigned long long n, uns
   acct_reduce_body<16u>(rec, n, nslots, dev_totals, ticket, page);
 }
 
-// Device-side timestamp record: one thread appends {slot, launches, globaltimer} -- used by the
-// stamp-kernel variant of segment marking (csrc/acct.cpp, GEMHOOK_STAMP=kernel) and by the bench's
-// primitive-cost probe.  kind: 0 = begin (subtract), 1 = end (add) -> totals += end - begin.
+// Device-side timestamp: slot_ns_signed[slot] += (kind ? +t : -t) with t = %globaltimer, so a begin/end pair adds
+// its duration.  NOT used by the hook in round 1 (segments are marked with CUDA events, gh_hook.cpp); kept as the
+// building block of the stamp-kernel marking listed in DESIGN.md 7 (a launch costs 2.05 us of host time on the
+// box, an event record 2.65 us plus a 2.7 us elapsed query).
 __global__ void gemhook_stamp(unsigned long long* __restrict__ slot_ns_signed, unsigned slot, unsigned kind) {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

@@ -9,7 +9,7 @@ aggregate launches/s over all devices and Jain's fairness index of delivered/ent
 delivered = the client's share of the device-timed run it spent inside its timed region and entitled = its
 min-fraction share.
 
-    python kubeshare_b200/tools/config5.py --gpus 8 --iters 40 [--impl ours|reference|both]
+    python kubeshare_b200/tools/scenario.py --gpus 8 --iters 40 [--impl ours|reference|both]
 """
 import argparse
 import json
