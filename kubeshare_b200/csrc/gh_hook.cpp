@@ -475,10 +475,15 @@ static void cuda_init_locked(gh_live* L) {
   }
   pthread_create(&L->trk_tid, nullptr, tracker_main, L);
   pthread_detach(L->trk_tid);
-  // first token request; its quota is discarded so that the first launch renews immediately (hook.cpp:766-768)
+  // first token request; its quota is discarded so that the first launch renews immediately (hook.cpp:766-768).
+  // It goes through the same one-at-a-time protocol as renewals: a second application thread arriving meanwhile
+  // waits on renew_cv instead of posting a competing request for the same slot.
+  L->renewing = true;
   pthread_mutex_unlock(&L->mu);
   token_from_scheduler(L, 0.0, 0.0);
   pthread_mutex_lock(&L->mu);
+  L->renewing = false;
+  pthread_cond_broadcast(&L->renew_cv);
 }
 
 // ---- launch slow path ---------------------------------------------------------------------------------
@@ -487,6 +492,7 @@ void gh_launch_slow(CUstream stream) {
   if (!L || !L->enabled) return;
   L->slow_path.fetch_add(1, std::memory_order_relaxed);
   pthread_mutex_lock(&L->mu);
+  while (L->renewing) pthread_cond_wait(&L->renew_cv, &L->mu);
   cuda_init_locked(L);
   while (L->renewing) pthread_cond_wait(&L->renew_cv, &L->mu);
   int64_t now = gh_now_ns();

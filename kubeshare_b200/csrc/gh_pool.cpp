@@ -627,6 +627,18 @@ GH_EXPORT double gemhook_pool_acquire(gemhook_pool* p, int slot, double overuse_
       return got;
     }
     if (++idle_rounds % 8 == 0) gemhook_pool_reap(p);  // a dead holder must not stall everybody until its deadline
+    if (me.state.load(std::memory_order_acquire) == ST_IDLE) {
+      // our request is gone without us having consumed a grant: another process of the same pod took it (they share
+      // the slot's mailbox), or a reaper cleared it.  Start over: the pod's token may already cover us.
+      p->lock();
+      if (!pod_launch_locked(p, slot, p->attach_idx, p->now_us(), overuse_ms, burst_ms, &fo, &fb, &remain)) {
+        p->unlock();
+        return remain;
+      }
+      request_locked(p, slot, p->now_ms(), fo, fb);
+      p->unlock();
+      continue;
+    }
     // someone else holds the token, or everyone is throttled: sleep on our own slot word until the hint
     // expires or a granter wakes us.  Short waits spin (no context switch on a quick hand-over).
     double wait_ms = (rc == 0 || rc == -2) ? sleep_ms : 0.2;

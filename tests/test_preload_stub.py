@@ -362,3 +362,21 @@ def test_yield_on_idle_hands_the_token_over_at_syncs():
     assert results[0][1] == 0 and results[1][1] >= 10          # tokens really changed hands at sync points
     assert results[1][2] > results[0][2]                         # ... which costs more (cheap) renewals
     assert results[1][0] < results[0][0] * 1.05                  # and never makes the pair slower
+
+
+def test_two_processes_of_one_pod_share_the_pods_token():
+    """Two processes with the SAME POD_NAME (one pod): gem-pmgr's pod-level token, one slot, one mailbox --
+    neither may starve or hang when their requests collide."""
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = []
+        for i in range(2):
+            env = hooked_env(tmp, pod="bench/c0", GEMHOOK_BASE_QUOTA_MS=5, GEMHOOK_MIN_QUOTA_MS=2,
+                             STUB_REPORT=os.path.join(tmp, "stub%d.json" % i))
+            procs.append(sp.Popen([kb.STORM_PATH, "--mode", "storm", "--steps", "6", "--warmup", "0", "--step-launches", "20000",
+                                   "--sync-every", "250", "--out", os.path.join(tmp, "out%d.json" % i)], env=env, stderr=sp.PIPE))
+        for p in procs:
+            _, err = p.communicate(timeout=120)
+            assert p.returncode == 0, err.decode()[-1000:]
+        st = stats_files(tmp)
+        assert len(st) == 2 and all(s["launches"] == 120000 for s in st)
+        assert sum(s["token_requests"] for s in st) >= 4
