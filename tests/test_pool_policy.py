@@ -352,3 +352,24 @@ def test_quota_file_sync_reloads_only_on_change():
         assert L.gemhook_pool_sync_quota_file(p, b"/nonexistent/file", 0) == -1
         L.gemhook_pool_close(q2)
         L.gemhook_pool_close(p)
+
+
+def test_quota_file_edge_cases():
+    """The file starts life as "0" (launcher-multigpus.sh:26-31) and is rewritten whole by kubeshare-config."""
+    L = kb.lib()
+    p = L.gemhook_pool_open(None, 1, 300.0, 20.0, 10000.0, 1)
+    assert L.gemhook_pool_load_config(p, b"0\n", 0) == 0 and L.gemhook_pool_nslots(p) == 0
+    assert L.gemhook_pool_load_config(p, b"", 0) == -1                      # no count at all
+    assert L.gemhook_pool_load_config(p, b"2\nns/a 0.5 1.0 10\n", 0) == -1  # count says 2, one row (torn write)
+    assert L.gemhook_pool_find(p, b"ns/a") == 0                              # ... the complete row was still taken
+    assert L.gemhook_pool_load_config(p, b"1\nns/a 0.25 0.75 99\n", 0) == 1  # re-read replaces the row in place
+    assert L.gemhook_pool_nslots(p) == 1
+    info = kb.SlotInfo()
+    L.gemhook_pool_slot_info(p, 0, info)
+    assert (info.min_frac, info.max_frac, info.mem_limit) == (0.25, 0.75, 99)
+    # 64 clients fit, the 65th does not
+    rows = "".join("ns/p%02d 0.01 1.0 1\n" % i for i in range(70))
+    assert L.gemhook_pool_load_config(p, ("70\n" + rows).encode(), 0) == -1
+    assert L.gemhook_pool_nslots(p) == 64
+    assert L.gemhook_pool_find(p, b"ns/p62") == 63 and L.gemhook_pool_find(p, b"ns/p69") == -1
+    L.gemhook_pool_close(p)
