@@ -98,6 +98,7 @@ struct gh_live {
   std::atomic<uint64_t> token_wait_ns{0};
   double accumulated_token_ms = 0;
   int64_t last_token_ns = 0;
+  int64_t token_returned_ns = 0;  // set when the token was handed back early (yield): the ledger entry ended there
   double last_quota_ms = 0;
 };
 
@@ -360,6 +361,7 @@ void gh_host_sync_post(void) {
     // launch storm that relaunches right after every sync keeps its token): hand it back; our next launch asks
     // again like any returning client.
     gemhook_gate_expire(L->gate);
+    L->token_returned_ns = L->last_sync_ns;
     L->yielded = true;
     yield = true;
     L->yields.fetch_add(1, std::memory_order_relaxed);
@@ -511,7 +513,9 @@ void gh_launch_slow(CUstream stream) {
     if (L->last_token_ns) {
       // what the scheduler's ledger will hold for the token we are returning:
       // end = min(now, start + quota + overuse) (reference scheduler.cpp:123-153)
-      double held = (double)(t_req - L->last_token_ns) / 1e6, cap = L->last_quota_ms + overuse;
+      int64_t t_end = L->token_returned_ns ? L->token_returned_ns : t_req;
+      L->token_returned_ns = 0;
+      double held = (double)(t_end - L->last_token_ns) / 1e6, cap = L->last_quota_ms + overuse;
       L->accumulated_token_ms += held < cap ? held : cap;
     }
     pthread_mutex_unlock(&L->mu);
