@@ -361,7 +361,11 @@ extern "C" __attribute__((visibility("default"))) const char* const* gemhook_hoo
   return kHookedNames;
 }
 
-// dlsym interposer (hook.cpp:109-159): anything that is not a hooked driver symbol goes to the libc dlsym
+// dlsym interposer (hook.cpp:109-159): anything that is not a hooked driver symbol goes to the libc dlsym.
+// The pass-through is a chain of sibling calls (dlsym -> gh_true_dlsym -> libc dlsym, all `jmp` at -O2, checked in
+// the disassembly), so glibc still sees the ORIGINAL caller's return address and dlsym(RTLD_NEXT, ...) issued by
+// other libraries keeps its meaning -- the reference calls the real dlsym from inside its own (hook.cpp:80-84,
+// 158), which re-anchors RTLD_NEXT at the hook library.
 __attribute__((no_sanitize("thread", "address", "undefined"))) void* dlsym(void* handle, const char* symbol) {
   if (symbol && symbol[0] == 'c' && symbol[1] == 'u') {
     if (!strcmp(symbol, "cuGetProcAddress_v2")) return (void*)&cuGetProcAddress_v2;
