@@ -196,9 +196,11 @@ struct gemhook_pool {
       uint32_t exp = 0;
       if (r->h.lock.compare_exchange_weak(exp, me, std::memory_order_acquire)) break;
       if (++spins > 2000) {
-        // owner may have died inside the critical section: steal after 100 ms
+        // owner may have died inside the critical section (it lasts microseconds): steal after a full second --
+        // long enough that a merely preempted owner is never robbed, short enough that a kill -9 landing exactly
+        // inside the section does not wedge the GPU's clients for good
         int64_t t = r->h.lock_ns.load(std::memory_order_relaxed);
-        if (t && gh_now_ns() - t > 100000000LL) {
+        if (t && gh_now_ns() - t > 1000000000LL) {
           if (r->h.lock.compare_exchange_strong(exp, me, std::memory_order_acquire)) break;
         }
         sched_yield();
