@@ -20,7 +20,12 @@ import orc
 import wireproto as wp
 
 REF = os.path.join(kb.ROOT, "oracle", "_ref")
-HAVE_REF = os.path.exists(os.path.join(REF, "gem-schd")) and os.path.exists(os.path.join(REF, "gem-pmgr"))
+
+
+def need_ref():
+    """oracle/_ref is built by the session fixture (needs /root/reference once); checked at run time, not import."""
+    if not (os.path.exists(os.path.join(REF, "gem-schd")) and os.path.exists(os.path.join(REF, "gem-pmgr"))):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
 GIB8 = 8589934592
 
 
@@ -167,9 +172,9 @@ def test_token_protocol_bytes_on_the_wire():
         mem[:3] == [(1000, 1), (2000, 1), (3000, 1)]
 
 
-@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
 def test_drop_in_against_live_reference_daemons():
     """Our hook speaking TCP to the UNMODIFIED gem-pmgr + gem-schd: tokens and the pod-wide memory cap."""
+    need_ref()
     with tempfile.TemporaryDirectory() as tmp:
         with open(os.path.join(tmp, "cfg.txt"), "w") as f:
             f.write("1\nbench/c0 1.0 1.0 5000\n")
@@ -244,8 +249,8 @@ def test_config4_memory_cap_sweep_pool():
         assert stats_files(tmp)[0]["mem_used"] == 0
 
 
-@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built (needs /root/reference)")
 def test_config4_memory_cap_sweep_against_live_gem_pmgr():
+    need_ref()
     with tempfile.TemporaryDirectory() as tmp:
         with open(os.path.join(tmp, "cfg.txt"), "w") as f:
             f.write("1\nbench/c0 1.0 1.0 %d\n" % GIB8)
