@@ -14,6 +14,15 @@
 static void* resolve_late(void** slot, const char* name) {
   if (gh_driver_init() != 0) return nullptr;
   void* p = gh_true_dlsym(gh_real.handle, name);
+  if (!p) {  // a driver without the per-thread-default-stream twin: fall back to the plain entry point
+    size_t n = strlen(name);
+    if (n > 5 && n < 96 && (!strcmp(name + n - 5, "_ptsz") || !strcmp(name + n - 5, "_ptds"))) {
+      char base[96];
+      memcpy(base, name, n - 5);
+      base[n - 5] = 0;
+      p = gh_true_dlsym(gh_real.handle, base);
+    }
+  }
   __atomic_store_n(slot, p, __ATOMIC_RELEASE);
   return p;
 }

@@ -298,13 +298,17 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 10; i++) CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
     for (int i = 0; i < 10; i++) CK(via_dlsym(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
     for (int i = 0; i < 10; i++) CK(via_gpa(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+    /* per-thread-default-stream flavour, as a cudart built with --default-stream per-thread asks for it */
+    launch_t via_gpa_pt = NULL;
+    CK(cuGetProcAddress("cuLaunchKernel", (void**)&via_gpa_pt, 12000, CU_GET_PROC_ADDRESS_PER_THREAD_DEFAULT_STREAM, &st));
+    for (int i = 0; i < 10; i++) CK(via_gpa_pt(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
     CK(cuCtxSynchronize());
     CUdeviceptr a = 0, b = 0, c = 0;
     CUresult r1 = cuMemAlloc(&a, 1000), r2 = alloc_dlsym(&b, 2000), r3 = alloc_gpa(&c, 3000);
     size_t fr = 0, tot = 0;
     cuMemGetInfo(&fr, &tot);
-    fprintf(out, "{\"mode\": \"resolve\", \"rc\": [%d, %d, %d], \"free\": %zu, \"total\": %zu, \"gpa_is_hooked\": %d}\n",
-            (int)r1, (int)r2, (int)r3, fr, tot, gpa_again != NULL);
+    fprintf(out, "{\"mode\": \"resolve\", \"rc\": [%d, %d, %d], \"free\": %zu, \"total\": %zu, \"gpa_is_hooked\": %d, \"ptsz_distinct\": %d}\n",
+            (int)r1, (int)r2, (int)r3, fr, tot, gpa_again != NULL, via_gpa_pt != via_gpa);
     free_gpa(c);
     cuMemFree(b);
     cuMemFree(a);

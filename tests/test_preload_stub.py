@@ -94,8 +94,8 @@ def test_all_three_binding_paths_are_hooked():
         env = hooked_env(tmp, quota="1\nbench/c0 1.0 1.0 5000\n")
         res = run_storm(env, "--mode", "resolve")
         st = stats_files(tmp)[0]
-        assert st["launches"] == 30               # direct + dlsym + cuGetProcAddress_v2
-        assert res["gpa_is_hooked"] == 1
+        assert st["launches"] == 40               # direct + dlsym + cuGetProcAddress_v2 (legacy and per-thread stream)
+        assert res["gpa_is_hooked"] == 1 and res["ptsz_distinct"] == 1
         # cap 5000 B: 1000 ok, 2000 ok, 3000 denied (1000+2000+3000 > 5000) on the cuGetProcAddress path
         assert res["rc"] == [0, 0, 2]             # CUDA_ERROR_OUT_OF_MEMORY == 2
         assert (res["free"], res["total"]) == (2000, 5000)   # virtualised cuMemGetInfo
@@ -106,7 +106,7 @@ def test_disabled_hook_is_transparent():
     with tempfile.TemporaryDirectory() as tmp:
         env = hooked_env(tmp, GEMHOOK_DISABLE=1)
         res = run_storm(env, "--mode", "resolve")
-        assert res["rc"] == [0, 0, 0] and res["total"] == 180 << 30
+        assert res["rc"] == [0, 0, 0] and res["total"] == 180 << 30   # interposed, but every call passes straight through
 
 
 # ------------------------------------------------------------------------------------------ wire / TCP
