@@ -276,3 +276,12 @@ print(json.dumps({"x0": float(x[0]), "total": total, "free_le_total": free <= to
     assert res["total"] == 2 << 30 and res["free_le_total"]
     assert st["launches"] >= 1500 and st["allocs_denied"] >= 1
     assert st["gpu_ns"] == st["gpu_ns_host"] > 0
+
+
+def test_binding_paths_on_real_driver():
+    """direct symbol, dlsym, cuGetProcAddress (legacy stream and per-thread stream) against the real libcuda."""
+    with tempfile.TemporaryDirectory() as tmp:
+        res = storm(env_pool(tmp, quota="1\nbench/c0 1.0 1.0 5000\n"), "--mode", "resolve")
+        st = stats(tmp)[0]
+    assert st["launches"] == 40 and res["gpa_is_hooked"] == 1 and res["ptsz_distinct"] == 1
+    assert res["rc"] == [0, 0, 2] and (res["free"], res["total"]) == (2000, 5000)
