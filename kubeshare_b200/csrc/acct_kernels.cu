@@ -80,6 +80,43 @@ __device__ __forceinline__ void bin_add(unsigned long long* ns, unsigned long lo
   }
 }
 
+// Last block of a launch (threadfence + ticket) publishes the running totals to the mapped pinned page.
+__device__ __forceinline__ void publish_totals(unsigned nslots, unsigned long long* __restrict__ dev_totals,
+                                               unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page) {
+  __shared__ unsigned is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicAdd(ticket, 1u);
+    is_last = (prev == gridDim.x - 1u) ? 1u : 0u;
+    if (is_last) *ticket = 0u;  // self-reset for the next launch (stream-ordered)
+  }
+  __syncthreads();
+  if (is_last && page) {
+    // Double-buffered publication: the totals go to the buffer the host is NOT reading (epoch parity), ONE
+    // system-scope fence orders them before the 8-byte epoch store that flips the reader over.  (A seqlock would
+    // need three fences across PCIe; the reader-side rule is in gh_acct.cpp read_page.)  The publish counter lives
+    // in device memory (dev_totals[nslots*3]) so nothing is ever READ over PCIe here.
+    __shared__ unsigned long long e_sh;
+    __threadfence();
+    if (threadIdx.x == 0) e_sh = *reinterpret_cast<volatile unsigned long long*>(dev_totals + nslots * 3u) + 1ull;
+    __syncthreads();
+    const unsigned long long e = e_sh;
+    unsigned long long* dst = page->buf[e & 1ull];
+    for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
+      // read through L2 (the atomics above were resolved there); volatile avoids a stale L1 line
+      dst[t] = *reinterpret_cast<volatile unsigned long long*>(dev_totals + t);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      dev_totals[nslots * 3u] = e;
+      page->nslots = nslots;
+      *reinterpret_cast<volatile unsigned long long*>(&page->epoch) = e;
+    }
+  }
+}
+
 // dev_totals: [nslots][3] u64 running totals + 1 u64 publish counter (device memory, persistent)
 // ticket:     u32 zero-initialised, self-resetting
 template <unsigned COLS>
@@ -176,40 +213,9 @@ __device__ __forceinline__ void acct_reduce_body(const uint4* __restrict__ rec, 
     if (acc) atomicAdd(dev_totals + t, acc);
   }
 
-  // last block publishes the running totals to the mapped pinned page
-  __shared__ unsigned is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned prev = atomicAdd(ticket, 1u);
-    is_last = (prev == gridDim.x - 1u) ? 1u : 0u;
-    if (is_last) *ticket = 0u;  // self-reset for the next launch (stream-ordered)
-  }
-  __syncthreads();
-  if (is_last && page) {
-    // Double-buffered publication: the totals go to the buffer the host is NOT reading (epoch parity), ONE
-    // system-scope fence orders them before the 8-byte epoch store that flips the reader over.  (A seqlock would
-    // need three fences across PCIe; the reader-side rule is in gh_acct.cpp read_page.)  The publish counter lives
-    // in device memory (dev_totals[nslots*3]) so nothing is ever READ over PCIe here.
-    __shared__ unsigned long long e_sh;
-    __threadfence();
-    if (threadIdx.x == 0) e_sh = *reinterpret_cast<volatile unsigned long long*>(dev_totals + nslots * 3u) + 1ull;
-    __syncthreads();
-    const unsigned long long e = e_sh;
-    unsigned long long* dst = page->buf[e & 1ull];
-    for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
-      // read through L2 (the atomics above were resolved there); volatile avoids a stale L1 line
-      dst[t] = *reinterpret_cast<volatile unsigned long long*>(dev_totals + t);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      dev_totals[nslots * 3u] = e;
-      page->nslots = nslots;
-      *reinterpret_cast<volatile unsigned long long*>(&page->epoch) = e;
-    }
-  }
+  publish_totals(nslots, dev_totals, ticket, page);
 }
+
 
 extern "C" {
 
