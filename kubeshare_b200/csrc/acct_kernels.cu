@@ -157,16 +157,15 @@ __device__ __forceinline__ void acct_reduce_body(const uint4* __restrict__ rec, 
 #pragma unroll
       for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add<COLS>(ns, la, rc, nslots, col, r[u]);
     } else {
-      if (lane < 16u) {
+      // lanes sharing a column take turns: phase p = lanes [p*COLS, (p+1)*COLS)
 #pragma unroll
-        for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add<COLS>(ns, la, rc, nslots, col, r[u]);
-      }
-      __syncwarp();
-      if (lane >= 16u) {
+      for (unsigned ph = 0; ph < 32u / COLS; ph++) {
+        if (lane / COLS == ph) {
 #pragma unroll
-        for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add<COLS>(ns, la, rc, nslots, col, r[u]);
+          for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add<COLS>(ns, la, rc, nslots, col, r[u]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   if (base < n) {  // ragged tail of this warp's last tile
@@ -178,10 +177,10 @@ __device__ __forceinline__ void acct_reduce_body(const uint4* __restrict__ rec, 
       if (COLS == 32u) {
         bin_add<COLS>(ns, la, rc, nslots, col, r);
       } else {
-        if (lane < 16u) bin_add<COLS>(ns, la, rc, nslots, col, r);
-        __syncwarp();
-        if (lane >= 16u) bin_add<COLS>(ns, la, rc, nslots, col, r);
-        __syncwarp();
+        for (unsigned ph = 0; ph < 32u / COLS; ph++) {
+          if (lane / COLS == ph) bin_add<COLS>(ns, la, rc, nslots, col, r);
+          __syncwarp();
+        }
       }
     }
   }

@@ -105,13 +105,17 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   if (nslots > 40) { a->cols = 16; a->warps = 2; cap_kb = 208; }
   else if (nslots > 24) { a->cols = 32; a->warps = 2; cap_kb = 208; }
   else if (nslots > 16) { a->cols = 16; a->warps = 4; cap_kb = 128; }
-  if (const char* e = getenv("GEMHOOK_ACCT_COLS")) a->cols = (unsigned)atoi(e) == 16u ? 16u : 32u;
+  if (const char* e = getenv("GEMHOOK_ACCT_COLS")) {
+    unsigned c = (unsigned)atoi(e);
+    if (c == 16u || c == 32u) a->cols = c;
+  }
   if (const char* e = getenv("GEMHOOK_ACCT_WARPS")) {
     unsigned w = (unsigned)atoi(e);
     if (w == 1u || w == 2u || w == 4u || w == 8u) a->warps = w;
   }
   if (const char* e = getenv("GEMHOOK_ACCT_SMEM_CAP_KB")) cap_kb = (unsigned)atoi(e);
-  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, a->cols == 32u ? "gemhook_acct_reduce" : "gemhook_acct_reduce_c16"));
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod,
+                 a->cols == 32u ? "gemhook_acct_reduce" : "gemhook_acct_reduce_c16"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_clear, a->mod, "gemhook_acct_clear"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_stamp, a->mod, "gemhook_stamp"));
   CU_TRY(GH_CALL(cuStreamCreate, &a->stream, CU_STREAM_NON_BLOCKING));
