@@ -12,7 +12,7 @@ def run_bench(nproc, extra_env=None):
     env = dict(os.environ, LD_LIBRARY_PATH=kb.STUB_DIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""),
                GEMBENCH_STEP_LAUNCHES="4096", STUB_KERNEL_US="1")
     env.update(extra_env or {})
-    args = ["bench.py", "--gpus", str(nproc), "--steps", "2", "--warmup", "3", "--clients", "1,2", "--skip-roofline",
+    args = ["bench.py", "--gpus", str(nproc), "--steps", "2", "--warmup", "3", "--clients", "1,2", "--reps", "2", "--skip-roofline",
             "--skip-baseline"]
     if nproc > 1:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
