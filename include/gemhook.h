@@ -56,9 +56,14 @@ extern "C" {
  *   Beyond the reference: cuLaunchKernelEx and cuGraphLaunch pass the token gate;
  *   cuMemAllocAsync / cuMemAllocFromPoolAsync / cuMemFreeAsync and cuMemCreate / cuMemRelease are charged against
  *   gpu_mem; every stream-taking hook has its _ptsz / _ptds twin; cuStreamSynchronize / cuEventSynchronize are
- *   exported and count as burst edges only with GEMHOOK_EXTRA_HOOKS=1.
+ *   exported and count as burst edges only with GEMHOOK_EXTRA_HOOKS=1; cuStreamDestroy_v2 closes an accounting
+ *   segment still open on the dying stream; cuMemAllocHost_v2 / cuMemHostAlloc / cuMemFreeHost are charged only with
+ *   GEMHOOK_ACCOUNT_HOST=1, cuMemAllocManaged / cuMipmappedArrayCreate only with GEMHOOK_ACCOUNT_MANAGED=1.
  */
 const char *const *gemhook_hooked_symbols(size_t *count); /* names above, NULL-terminated */
+/* per-symbol call counters, kept when CU_HOOK_DEBUG=1 (hook.cpp:87-100, 783, 991). Returns the number of counters;
+ * names is NULL-terminated. */
+size_t gemhook_call_counts(const char *const **names, const uint64_t **counts);
 
 /* ===================================================================================================
  * (2a) wire codec -- comm.h:28-31, comm.cpp:26-120
@@ -160,6 +165,9 @@ size_t gemhook_pool_history(const gemhook_pool *, int *slots, double *starts, do
 double gemhook_pool_accumulated_ms(const gemhook_pool *, int slot);
 /* blocking convenience used by the live hook: post request, arbitrate, wait for the grant. */
 double gemhook_pool_acquire(gemhook_pool *, int slot, double overuse_ms, double burst_ms);
+/* same; *forwarded (optional) = 1 if the request went to the scheduler policy (the reply is the client's new adaptive
+ * quota), 0 if the pod-level rule answered it with the remaining pod quota (pod-manager.cpp:472). */
+double gemhook_pool_acquire_ex(gemhook_pool *, int slot, double overuse_ms, double burst_ms, int *forwarded);
 /* hand an outstanding token back early (client exit); the next waiter is scheduled immediately. */
 void gemhook_pool_release(gemhook_pool *, int slot);
 /* 1 if another client is waiting for the token (lock-free peek). */
@@ -200,6 +208,8 @@ void gemhook_pool_mem_info(const gemhook_pool *, int slot, uint64_t *used, uint6
 
 /* byte rules for arrays / pitch (hook.cpp:629-680) */
 uint64_t gemhook_array_bytes(uint64_t w, uint64_t h, uint64_t d, uint32_t channels, uint32_t format, int is3d);
+/* opt-in (GEMHOOK_ACCOUNT_MANAGED=1) charge for a mipmapped array: the rule above per level, extents halving. */
+uint64_t gemhook_mipmap_bytes(uint64_t w, uint64_t h, uint64_t d, uint32_t channels, uint32_t format, uint32_t levels);
 
 /* ===================================================================================================
  * (2d) device accounting -- the sm_100a reduction over 16-byte launch records

@@ -92,6 +92,7 @@ def lib():
         "gemhook_pool_history": (sz, [vp, pi, pd, pd, sz]),
         "gemhook_pool_accumulated_ms": (d, [vp, C.c_int]),
         "gemhook_pool_acquire": (d, [vp, C.c_int, d, d]),
+        "gemhook_pool_acquire_ex": (d, [vp, C.c_int, d, d, pi]),
         "gemhook_pool_release": (None, [vp, C.c_int]),
         "gemhook_pool_expire_token": (None, [vp]), "gemhook_pool_others_waiting": (C.c_int, [vp, C.c_int]),
         "gemhook_pool_slot_info": (C.c_int, [vp, C.c_int, C.POINTER(SlotInfo)]),
@@ -103,6 +104,8 @@ def lib():
         "gemhook_pool_mem_release": (None, [vp, C.c_int, u64]),
         "gemhook_pool_mem_info": (None, [vp, C.c_int, C.POINTER(u64), C.POINTER(u64)]),
         "gemhook_array_bytes": (u64, [u64, u64, u64, u32, u32, C.c_int]),
+        "gemhook_mipmap_bytes": (u64, [u64, u64, u64, u32, u32, u32]),
+        "gemhook_call_counts": (sz, [C.POINTER(C.POINTER(cp)), C.POINTER(C.POINTER(u64))]),
         "gemhook_acct_create": (vp, [u32, sz]), "gemhook_acct_destroy": (None, [vp]),
         "gemhook_acct_reduce_host": (C.c_int, [vp, vp, sz, vp]),
         "gemhook_acct_reduce_device": (C.c_int, [vp, u64, sz, C.POINTER(C.c_float)]),

@@ -222,9 +222,9 @@ GH_EXPORT int gemhook_acct_reduce_device(gemhook_acct* a, uint64_t d_records, si
 }
 
 static int read_page(gemhook_acct* a, uint64_t* totals_out, uint64_t* epoch_out) {
-  // The device writes buf[(e+1) & 1] and then stores epoch = e+1.  A copy of buf[e & 1] taken while the epoch
-  // moved from e to e+1 is still intact (the writer touched the other buffer); only a move of two or more
-  // may have overwritten it -> retry.
+  // The device writes buf[(e+1) & 1], fences, then stores epoch = e+1.  A copy of buf[e & 1] is intact only if the
+  // epoch did not move at all while it was taken: once the epoch reads e+1, kernel e+2 may already be filling
+  // buf[(e+2) & 1] -- the very buffer being copied.  Anything else -> retry (a flush is microseconds apart at worst).
   for (int tries = 0; tries < 1000000; tries++) {
     uint64_t e1 = a->page->epoch;
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
@@ -235,7 +235,7 @@ static int read_page(gemhook_acct* a, uint64_t* totals_out, uint64_t* epoch_out)
     }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
     uint64_t e2 = a->page->epoch;
-    if (e2 - e1 <= 1) {
+    if (e2 == e1) {
       if (epoch_out) *epoch_out = e1;
       return 0;
     }

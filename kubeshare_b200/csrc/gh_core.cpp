@@ -11,6 +11,7 @@
 int gh_log_level = 0;
 gh_driver gh_real;
 gh_config gh_cfg;
+uint32_t gh_hook_debug = 0;
 
 static __thread char tls_error[512];
 static char g_error[512];
@@ -112,6 +113,8 @@ void gh_config_load(void) {
   if (lvl) gh_log_level = atoi(lvl);
   const char* dbg = getenv("CU_HOOK_DEBUG");  // reference hook.cpp:96
   if (dbg && dbg[0] == '1' && gh_log_level < 2) gh_log_level = 2;
+  c.hook_debug = (dbg && dbg[0] == '1') ? 1 : 0;
+  __atomic_store_n(&gh_hook_debug, (uint32_t)c.hook_debug, __ATOMIC_RELAXED);
 
   const char* pn = getenv("POD_NAME");
   if (pn && *pn) snprintf(c.pod_name, sizeof(c.pod_name), "%s", pn);
@@ -148,4 +151,7 @@ void gh_config_load(void) {
   c.disabled = (int)env_i("GEMHOOK_DISABLE", 0);
   c.yield_on_idle = (int)env_i("GEMHOOK_YIELD_ON_IDLE", 0);
   c.yield_min_idle_ms = env_f("GEMHOOK_YIELD_MIN_IDLE_MS", 0.5);
+  c.account_managed = (int)env_i("GEMHOOK_ACCOUNT_MANAGED", 0);
+  c.account_host = (int)env_i("GEMHOOK_ACCOUNT_HOST", 0);
+  env_str("GEMHOOK_TOKEN_TRACE", c.token_trace, sizeof(c.token_trace), "");
 }

@@ -26,7 +26,7 @@
 
 int gh_rpc(gemhook_request* req, gemhook_response* rsp);
 int gh_acct_push_async(gemhook_acct* a, const gemhook_record* pinned_records, size_t n);
-void gh_pool_publish_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches);
+void gh_pool_add_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches);
 void* gh_pool_region(gemhook_pool* p, size_t* bytes);
 
 uint32_t gh_gate_open = 0;  // accessed with relaxed __atomic builtins only (plain MOVs on x86, race-free by the book)
@@ -100,6 +100,18 @@ struct gh_live {
   int64_t last_token_ns = 0;
   int64_t token_returned_ns = 0;  // set when the token was handed back early (yield): the ledger entry ended there
   double last_quota_ms = 0;
+  bool token_ev_valid = false;  // ev_token was recorded for the running token (not while a stream capture was active)
+
+  // live publication of the device-reduced usage into the pool slot (what exporters scrape)
+  uint64_t pub_epoch = 0, pub_ns = 0, pub_launches = 0;
+
+  // GEMHOOK_TOKEN_TRACE: (t, overuse, burst) -> quota of every token request, kept in memory, written at exit
+  struct TokenTrace {
+    double t_ms, overuse_ms, burst_ms, quota_ms;
+    int forwarded;
+  };
+  TokenTrace* trace = nullptr;
+  uint32_t trace_n = 0, trace_cap = 0;
 };
 
 static gh_live* g_live = nullptr;
@@ -112,13 +124,40 @@ static void fatal_or_disable(gh_live* L, const char* what) {
   L->enabled = false;
 }
 
+// A stream that is being captured into a CUDA graph must not see our events: they would become event-record
+// nodes of the application's graph, be re-recorded at every replay, and an elapsed-time query on them fails the
+// capture.  The legacy stream cannot be captured itself, but touching it while a BLOCKING stream captures is an
+// implicit dependency that invalidates the application's capture -- cuStreamIsCapturing(legacy) reports exactly
+// that case with an error and does not invalidate anything (driver API docs).  The reference never looks
+// (hook.cpp:482-485, 543 record on the legacy stream unconditionally).
+static bool stream_capturing(CUstream s) {
+  if (!gh_real.cuStreamIsCapturing) return false;
+  CUstreamCaptureStatus st = CU_STREAM_CAPTURE_STATUS_NONE;
+  CUresult r = GH_CALL(cuStreamIsCapturing, s, &st);
+  return r != CUDA_SUCCESS || st != CU_STREAM_CAPTURE_STATUS_NONE;
+}
+
+// device totals -> pool slot, as deltas (several processes of one pod add into the same slot).  The totals page is
+// read without any CUDA call; it reflects every reduce kernel that has completed.  Caller holds L->mu.
+static void publish_usage_locked(gh_live* L) {
+  if (!L->acct || !L->pool) return;
+  uint64_t tot[GEMHOOK_MAX_SLOTS * 3], ep = 0;
+  if (gemhook_acct_read_totals(L->acct, tot, &ep) != 0 || ep == L->pub_epoch) return;
+  uint64_t ns = tot[L->slot * 3], la = tot[L->slot * 3 + 1];
+  gh_pool_add_usage(L->pool, L->slot, ns - L->pub_ns, la - L->pub_launches);
+  L->pub_epoch = ep;
+  L->pub_ns = ns;
+  L->pub_launches = la;
+}
+
 // ---- token transport ----------------------------------------------------------------------------------
 static double token_from_scheduler(gh_live* L, double overuse_ms, double next_burst_ms) {
   L->token_requests.fetch_add(1, std::memory_order_relaxed);
   int64_t t0 = gh_now_ns();
   double q = 0.0;
+  int forwarded = -1;  // unknown over TCP: gem-pmgr decides (pod-manager.cpp:316-473)
   if (gh_cfg.transport == 1) {
-    q = gemhook_pool_acquire(L->pool, L->slot, overuse_ms, next_burst_ms);
+    q = gemhook_pool_acquire_ex(L->pool, L->slot, overuse_ms, next_burst_ms, &forwarded);
   } else {
     gemhook_request req;
     gemhook_response rsp;
@@ -134,6 +173,8 @@ static double token_from_scheduler(gh_live* L, double overuse_ms, double next_bu
   }
   L->token_wait_ns.fetch_add((uint64_t)(gh_now_ns() - t0), std::memory_order_relaxed);
   GH_DEBUG("token: overuse %.3f ms, next burst %.3f ms -> quota %.3f ms", overuse_ms, next_burst_ms, q);
+  if (L->trace && L->trace_n < L->trace_cap)
+    L->trace[L->trace_n++] = {(double)t0 / 1e6, overuse_ms, next_burst_ms, q, forwarded};
   return q;
 }
 
@@ -145,6 +186,12 @@ static void sync_pre(bool force);
 static void* tracker_main(void* arg) {
   gh_live* L = (gh_live*)arg;
   GH_CALL(cuCtxSetCurrent, L->ctx);
+  if (gh_real.cuThreadExchangeStreamCaptureMode) {
+    // this thread's driver calls must never be judged against (or invalidate) a capture the application runs in
+    // global mode on another thread
+    CUstreamCaptureMode m = CU_STREAM_CAPTURE_MODE_RELAXED;
+    GH_CALL(cuThreadExchangeStreamCaptureMode, &m);
+  }
   for (;;) {
     pthread_mutex_lock(&L->trk_mu);
     while (!L->trk_armed) pthread_cond_wait(&L->trk_start_cv, &L->trk_mu);
@@ -162,17 +209,21 @@ static void* tracker_main(void* arg) {
     // drain everything issued so far: an event on the legacy default stream waits for all blocking
     // streams (hook.cpp:449-453, 482-485); the events are reused, not leaked per token.
     float elapsed_ms = 0.f;
+    bool measured = false;
     if (!gh_cfg.dry_run) {
       sync_pre(true);  // close the running accounting segment on its own stream first
-      GH_CALL(cuEventRecord, L->ev_drain, (CUstream)0);
-      GH_CALL(cuEventSynchronize, L->ev_drain);
-      GH_CALL(cuEventElapsedTime, &elapsed_ms, L->ev_token, L->ev_drain);
+      // while the application captures a graph the legacy stream is off limits: fall back to the host clock
+      if (L->token_ev_valid && !stream_capturing((CUstream)0) &&
+          GH_CALL(cuEventRecord, L->ev_drain, (CUstream)0) == CUDA_SUCCESS &&
+          GH_CALL(cuEventSynchronize, L->ev_drain) == CUDA_SUCCESS &&
+          GH_CALL(cuEventElapsedTime, &elapsed_ms, L->ev_token, L->ev_drain) == CUDA_SUCCESS)
+        measured = true;
     }
     pthread_mutex_lock(&L->mu);
     int64_t now = gh_now_ns();
     host_sync_locked(L, now);  // burst ends here; next launch re-evaluates the token
     if (L->yielded) elapsed_ms = 0.f;  // token given back early: nothing was overused
-    else if (gh_cfg.dry_run) elapsed_ms = (float)((double)(now - L->last_token_ns) / 1e6);
+    else if (!measured) elapsed_ms = (float)((double)(now - L->last_token_ns) / 1e6);
     L->yielded = false;
     gemhook_gate_tracker_fire(L->gate, now, elapsed_ms);
     if (L->cuda_ready && !gh_cfg.dry_run) resolve_pending_locked(L, false);
@@ -238,7 +289,11 @@ static void seg_begin_locked(gh_live* L, CUstream stream) {
   if (L->seg_open && L->seg_spans_sync) {  // the running segment continues across the sync we just passed
     if (L->seg_sync_return_ns && now > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(now - L->seg_sync_return_ns);
     L->seg_spans_sync = false;
-    L->seg_stream = stream;
+    if (!stream_capturing(stream)) L->seg_stream = stream;  // (its end marker must go to a stream we may record on)
+    return;
+  }
+  if (stream_capturing(stream)) {  // launches into a capturing stream do not run now: nothing to time
+    L->seg_open = false;
     return;
   }
   L->seg_head = (L->seg_head + 1) % SEG_EVENTS;
@@ -257,7 +312,7 @@ void gh_segment_tick(CUstream stream) {
   gh_live* L = g_live;
   if (!L || !L->cuda_ready || gh_cfg.dry_run) return;
   pthread_mutex_lock(&L->mu);
-  if (L->seg_open && L->npending < SEG_EVENTS / 2 - 1) {
+  if (L->seg_open && L->npending < SEG_EVENTS / 2 - 1 && !stream_capturing(stream)) {
     int nxt = (L->seg_head + 1) % SEG_EVENTS;
     if (GH_CALL(cuEventRecord, L->seg_ev[nxt], stream) == CUDA_SUCCESS) {
       uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
@@ -286,6 +341,9 @@ static void sync_pre(bool force) {
   bool old_enough = force || (gh_now_ns() - L->seg_begin_host_ns >= (int64_t)gh_cfg.seg_min_us * 1000);
   if (L->seg_open && !L->seg_end_recorded && !old_enough) {
     L->seg_spans_sync = true;  // keep it open across this sync
+  } else if (L->seg_open && !L->seg_end_recorded && stream_capturing(L->seg_stream)) {
+    L->seg_open = false;  // its stream went into capture mode meanwhile: the segment cannot be closed there, drop it
+    L->seg_spans_sync = false;
   } else if (L->seg_open && !L->seg_end_recorded && L->npending < SEG_EVENTS - 2) {
     if (L->seg_spans_sync && L->seg_sync_return_ns) {  // forced close while idle after a merged sync
       int64_t t = gh_now_ns();
@@ -308,9 +366,36 @@ static void sync_pre(bool force) {
   // 1024-launch burst).
   resolve_pending_locked(L, false, fresh);
   flush_stage_locked(L, false);
+  publish_usage_locked(L);  // totals of the reduce kernels that have completed so far -> pool slot (live export)
   pthread_mutex_unlock(&L->mu);
 }
 void gh_host_sync_pre(void) { sync_pre(false); }
+
+// cuStreamDestroy pre-hook: the stream is still valid here, so a segment open on it gets its end marker now
+// (afterwards L->seg_stream would dangle -- the tracker thread records on it).
+void gh_stream_destroyed(CUstream stream) {
+  gh_live* L = g_live;
+  if (!L || !L->cuda_ready || gh_cfg.dry_run || !stream) return;
+  pthread_mutex_lock(&L->mu);
+  if (L->seg_open && !L->seg_end_recorded && L->seg_stream == stream) {
+    int nxt = (L->seg_head + 1) % SEG_EVENTS;
+    if (L->npending < SEG_EVENTS - 2 && !stream_capturing(stream) &&
+        GH_CALL(cuEventRecord, L->seg_ev[nxt], stream) == CUDA_SUCCESS) {
+      if (L->seg_spans_sync && L->seg_sync_return_ns) {
+        int64_t t = gh_now_ns();
+        if (t > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(t - L->seg_sync_return_ns);
+      }
+      uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+      L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch), L->seg_idle_ns};
+      L->seg_head = nxt;
+    }
+    L->seg_open = false;
+    L->seg_spans_sync = false;
+    __atomic_store_n(&gh_gate_open, 0u, __ATOMIC_RELAXED);  // the next launch opens a fresh segment on its own stream
+  }
+  if (L->seg_stream == stream) L->seg_stream = nullptr;
+  pthread_mutex_unlock(&L->mu);
+}
 
 // all pending events are complete after a host sync: turn them into records
 static void resolve_pending_locked(gh_live* L, bool may_block, int skip_last) {
@@ -423,6 +508,11 @@ static void live_init(void) {
     // reference: exit(-1) when /kubeshare/library/schedulerIP.txt is missing (hook.cpp:234-237)
     fatal_or_disable(L, "scheduler IP file missing (set GEMHOOK_SCHEDULER_IP or /kubeshare/library/schedulerIP.txt)");
   }
+  if (gh_cfg.token_trace[0]) {
+    L->trace_cap = 1u << 16;
+    L->trace = (gh_live::TokenTrace*)calloc(L->trace_cap, sizeof(gh_live::TokenTrace));
+    if (!L->trace) L->trace_cap = 0;
+  }
   g_live = L;
   if (!L->enabled) __atomic_store_n(&gh_gate_open, 1u, __ATOMIC_RELAXED);
   // registered after the driver's own atexit handlers (cuInit ran before the first intercepted call),
@@ -522,7 +612,9 @@ void gh_launch_slow(CUstream stream) {
     if (L->pool) read_quota_file_into_pool(L);  // one stat() per token: pick up kubeshare-config's rewrites
     double quota = token_from_scheduler(L, overuse, next_burst);
     pthread_mutex_lock(&L->mu);
-    if (!gh_cfg.dry_run) GH_CALL(cuEventRecord, L->ev_token, (CUstream)0);  // hook.cpp:543
+    // hook.cpp:543 records on the legacy stream; not while the application captures (see stream_capturing)
+    L->token_ev_valid = !gh_cfg.dry_run && !stream_capturing((CUstream)0) &&
+                        GH_CALL(cuEventRecord, L->ev_token, (CUstream)0) == CUDA_SUCCESS;
     now = gh_now_ns();
     gemhook_gate_renew_granted(L->gate, now, quota);
     L->last_token_ns = now;
@@ -558,11 +650,7 @@ GH_EXPORT int gemhook_flush(void) {
   }
   resolve_pending_locked(L, true);
   flush_stage_locked(L, true);
-  if (L->acct && L->pool) {
-    uint64_t tot[GEMHOOK_MAX_SLOTS * 3];
-    if (gemhook_acct_read_totals(L->acct, tot, nullptr) == 0)
-      gh_pool_publish_usage(L->pool, L->slot, tot[L->slot * 3], tot[L->slot * 3 + 1]);
-  }
+  publish_usage_locked(L);
   pthread_mutex_unlock(&L->mu);
   return 0;
 }
@@ -597,15 +685,29 @@ GH_EXPORT int gemhook_get_stats(gemhook_stats* out) {
 // by bench.py and the tests to collect per-client numbers without touching the application.
 uint64_t gh_mem_denied(void);
 void gh_register_exit_hook(void);
+static void write_token_trace(gh_live* L) {
+  if (!L->trace || !gh_cfg.token_trace[0]) return;
+  char path[600];
+  snprintf(path, sizeof(path), gh_cfg.token_trace, (int)getpid());
+  FILE* f = fopen(path, "w");
+  if (!f) return;
+  for (uint32_t i = 0; i < L->trace_n; i++)
+    fprintf(f, "{\"pod\": \"%s\", \"t_ms\": %.6f, \"overuse_ms\": %.17g, \"burst_ms\": %.17g, \"quota_ms\": %.17g, \"forwarded\": %d}\n", gh_cfg.pod_name,
+            L->trace[i].t_ms, L->trace[i].overuse_ms, L->trace[i].burst_ms, L->trace[i].quota_ms, L->trace[i].forwarded);
+  fclose(f);
+}
+
 static void write_stats_file(void) {
   const char* pat = getenv("GEMHOOK_STATS_FILE");
   gh_live* L = g_live;
-  if (L && L->enabled && L->pool) {
-    gemhook_pool_release(L->pool, L->slot);  // do not make peers wait for a timeout
+  if (!L) return;
+  gemhook_flush();  // the last segments reach the device totals and the pool slot whether or not anybody asked for a file
+  if (L->enabled && L->pool) {
+    gemhook_pool_release(L->pool, L->slot);  // do not make peers wait for a timeout (no-op while a sibling process runs)
     gemhook_pool_detach(L->pool);            // bytes this process never freed go back to the pod's budget
   }
-  if (!pat || !*pat || !L) return;
-  gemhook_flush();
+  write_token_trace(L);
+  if (!pat || !*pat) return;
   gemhook_stats s;
   gemhook_get_stats(&s);
   char path[600];
@@ -616,13 +718,22 @@ static void write_stats_file(void) {
           "{\"pod\": \"%s\", \"pid\": %d, \"launches\": %llu, \"fast_path\": %llu, \"slow_path\": %llu, "
           "\"token_requests\": %llu, \"host_syncs\": %llu, \"segments\": %llu, \"acct_kernels\": %llu, "
           "\"gpu_ns\": %llu, \"gpu_ns_host\": %llu, \"mem_used\": %llu, \"mem_limit\": %llu, \"allocs_denied\": %llu, "
-          "\"quota_ms\": %.6f, \"overuse_ms\": %.6f, \"token_wait_ms\": %.6f, \"accumulated_token_ms\": %.6f, \"yields\": %llu}\n",
+          "\"quota_ms\": %.6f, \"overuse_ms\": %.6f, \"token_wait_ms\": %.6f, \"accumulated_token_ms\": %.6f, \"yields\": %llu",
           gh_cfg.pod_name, (int)getpid(), (unsigned long long)s.launches, (unsigned long long)s.fast_path,
           (unsigned long long)s.slow_path, (unsigned long long)s.token_requests, (unsigned long long)s.host_syncs,
           (unsigned long long)s.segments, (unsigned long long)s.acct_kernels, (unsigned long long)s.gpu_ns,
           (unsigned long long)L->gpu_ns_host, (unsigned long long)s.mem_used, (unsigned long long)s.mem_limit,
           (unsigned long long)gh_mem_denied(), s.quota_ms, s.overuse_ms, s.token_wait_ms, s.accumulated_token_ms,
           (unsigned long long)L->yields.load());
+  if (gh_cfg.hook_debug) {  // CU_HOOK_DEBUG=1: the per-symbol call counters (reference hookInfo::call_count)
+    const char* const* names = nullptr;
+    const uint64_t* counts = nullptr;
+    size_t n = gemhook_call_counts(&names, &counts);
+    fprintf(f, ", \"calls\": {");
+    for (size_t i = 0; i < n; i++) fprintf(f, "%s\"%s\": %llu", i ? ", " : "", names[i], (unsigned long long)counts[i]);
+    fprintf(f, "}");
+  }
+  fprintf(f, "}\n");
   fclose(f);
 }
 

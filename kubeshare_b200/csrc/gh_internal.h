@@ -36,12 +36,13 @@ static inline int64_t gh_now_ns(void) {
   X(cuDeviceGetAttribute) X(cuDeviceTotalMem_v2) X(cuMemGetInfo_v2)                                    \
   X(cuModuleLoadData) X(cuModuleGetFunction) X(cuModuleUnload) X(cuFuncSetAttribute)                  \
   X(cuOccupancyMaxActiveBlocksPerMultiprocessor)                                                       \
-  X(cuStreamCreate) X(cuStreamDestroy_v2) X(cuStreamSynchronize)                                       \
+  X(cuStreamCreate) X(cuStreamDestroy_v2) X(cuStreamSynchronize) X(cuStreamIsCapturing)                  \
+  X(cuThreadExchangeStreamCaptureMode)                                                                 \
   X(cuEventCreate) X(cuEventDestroy_v2) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime)   \
   X(cuEventQuery)                                                                                      \
   X(cuMemAlloc_v2) X(cuMemFree_v2) X(cuMemAllocManaged) X(cuMemAllocPitch_v2)                          \
   X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2) X(cuMemsetD8Async)                                   \
-  X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostGetDevicePointer_v2)                                   \
+  X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostGetDevicePointer_v2) X(cuMemAllocHost_v2)                 \
   X(cuMemHostRegister_v2) X(cuMemHostUnregister)                                                       \
   X(cuLaunchKernel) X(cuLaunchCooperativeKernel)                                                       \
   X(cuArrayCreate_v2) X(cuArray3DCreate_v2) X(cuArrayDestroy)                                          \
@@ -77,8 +78,10 @@ void gh_host_sync_pre(void);
 void gh_host_sync_post(void);
 extern uint32_t gh_gate_open;              // 1: burst ongoing and token valid -> fast path (relaxed atomics)
 extern uint64_t gh_launch_count;           // intercepted launches (relaxed)
+extern uint32_t gh_hook_debug;            // CU_HOOK_DEBUG=1: count calls per symbol (relaxed atomics; set once by the config load)
 extern uint32_t gh_seg_mask;               // segment every (mask+1) launches; 0xffffffff = burst edges only
 void gh_segment_tick(CUstream stream);
+void gh_stream_destroyed(CUstream stream);  // cuStreamDestroy pre-hook: a segment open on that stream is closed first
 
 // gpu_mem cap (gh_mem.cpp)
 int gh_mem_reserve(uint64_t bytes);        // 1 ok, 0 denied
@@ -106,6 +109,10 @@ struct gh_config {
   int disabled;
   double yield_min_idle_ms;  // ... only when the window predictor expects at least this much idle time
   int yield_on_idle;      // hand the token back at a host sync when another client is waiting (work-conserving option)
+  int account_managed;    // GEMHOOK_ACCOUNT_MANAGED=1: charge cuMemAllocManaged / mipmapped arrays (the reference does not)
+  int account_host;       // GEMHOOK_ACCOUNT_HOST=1: charge cuMemAllocHost / cuMemHostAlloc (pinned host memory) too
+  int hook_debug;         // CU_HOOK_DEBUG=1 (reference hook.cpp:93-100): per-symbol call counters
+  char token_trace[512];  // GEMHOOK_TOKEN_TRACE=<path, %d = pid>: one JSON line per token request, written at exit
 };
 extern gh_config gh_cfg;
 void gh_config_load(void);

@@ -10,6 +10,37 @@
 
 #define GH_HOOK extern "C" __attribute__((visibility("default"))) CUresult CUDAAPI
 
+// CU_HOOK_DEBUG=1: per-symbol call counters (reference hook.cpp:87-100, 783, 860, 868, 991 keep the same counts in
+// hookInfo::call_count and never print them; ours are readable through gemhook_call_counts()).
+#define GH_COUNTED(X)                                                                                              \
+  X(cuLaunchKernel) X(cuLaunchCooperativeKernel) X(cuLaunchKernelEx) X(cuGraphLaunch) X(cuMemAlloc) X(cuMemAllocManaged) \
+  X(cuMemAllocPitch) X(cuMemFree) X(cuArrayCreate) X(cuArray3DCreate) X(cuMipmappedArrayCreate) X(cuArrayDestroy)  \
+  X(cuMipmappedArrayDestroy) X(cuMemGetInfo) X(cuDeviceTotalMem) X(cuCtxSynchronize) X(cuMemcpyAtoH)               \
+  X(cuMemcpyDtoH) X(cuMemcpyHtoA) X(cuMemcpyHtoD) X(cuMemAllocAsync) X(cuMemAllocFromPoolAsync) X(cuMemFreeAsync)   \
+  X(cuMemCreate) X(cuMemRelease) X(cuStreamSynchronize) X(cuEventSynchronize) X(cuStreamDestroy) X(cuMemAllocHost) \
+  X(cuMemHostAlloc) X(cuMemFreeHost) X(cuGetProcAddress) X(dlsym)
+enum {
+#define X(n) CNT_##n,
+  GH_COUNTED(X)
+#undef X
+  CNT_MAX
+};
+static uint64_t g_calls[CNT_MAX];
+static const char* const g_call_names[CNT_MAX + 1] = {
+#define X(n) #n,
+    GH_COUNTED(X)
+#undef X
+    nullptr};
+#define GH_COUNT(n)                                                                                   \
+  do {                                                                                                \
+    if (__builtin_expect(__atomic_load_n(&gh_hook_debug, __ATOMIC_RELAXED), 0)) __atomic_add_fetch(&g_calls[CNT_##n], 1, __ATOMIC_RELAXED); \
+  } while (0)
+extern "C" __attribute__((visibility("default"))) size_t gemhook_call_counts(const char* const** names, const uint64_t** counts) {
+  if (names) *names = g_call_names;
+  if (counts) *counts = g_calls;
+  return CNT_MAX;
+}
+
 // late resolution for names that are not part of the core table (ptsz/ptds twins, Ex)
 static void* resolve_late(void** slot, const char* name) {
   if (gh_driver_init() != 0) return nullptr;
@@ -48,11 +79,13 @@ typedef CUresult(CUDAAPI* launchex_fn)(const CUlaunchConfig*, CUfunction, void**
 
 GH_HOOK cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
                        unsigned shmem, CUstream hStream, void** params, void** extra) {
+  GH_COUNT(cuLaunchKernel);
   launch_gate(hStream);
   return GH_REAL_CORE(cuLaunchKernel)(f, gx, gy, gz, bx, by, bz, shmem, hStream, params, extra);
 }
 GH_HOOK cuLaunchCooperativeKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
                                   unsigned bz, unsigned shmem, CUstream hStream, void** params) {
+  GH_COUNT(cuLaunchCooperativeKernel);
   launch_gate(hStream);
   return GH_REAL_CORE(cuLaunchCooperativeKernel)(f, gx, gy, gz, bx, by, bz, shmem, hStream, params);
 }
@@ -65,25 +98,30 @@ static void* p_launchex_ptsz;
 
 GH_HOOK cuLaunchKernel_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
                             unsigned shmem, CUstream hStream, void** params, void** extra) {
+  GH_COUNT(cuLaunchKernel);
   launch_gate(hStream);
   return ((launch_fn)LATE(p_launch_ptsz, "cuLaunchKernel_ptsz"))(f, gx, gy, gz, bx, by, bz, shmem, hStream, params, extra);
 }
 GH_HOOK cuLaunchCooperativeKernel_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
                                        unsigned bz, unsigned shmem, CUstream hStream, void** params) {
+  GH_COUNT(cuLaunchCooperativeKernel);
   launch_gate(hStream);
   return ((coop_fn)LATE(p_coop_ptsz, "cuLaunchCooperativeKernel_ptsz"))(f, gx, gy, gz, bx, by, bz, shmem, hStream, params);
 }
 GH_HOOK cuLaunchKernelEx(const CUlaunchConfig* config, CUfunction f, void** params, void** extra) {
+  GH_COUNT(cuLaunchKernelEx);
   launch_gate(config ? config->hStream : nullptr);
   return ((launchex_fn)LATE(p_launchex, "cuLaunchKernelEx"))(config, f, params, extra);
 }
 GH_HOOK cuLaunchKernelEx_ptsz(const CUlaunchConfig* config, CUfunction f, void** params, void** extra) {
+  GH_COUNT(cuLaunchKernelEx);
   launch_gate(config ? config->hStream : nullptr);
   return ((launchex_fn)LATE(p_launchex_ptsz, "cuLaunchKernelEx_ptsz"))(config, f, params, extra);
 }
 
 // ---- gpu_mem cap ----------------------------------------------------------------------------------------
 GH_HOOK cuMemAlloc_v2(CUdeviceptr* dptr, size_t bytesize) {
+  GH_COUNT(cuMemAlloc);
   if (!gh_mem_reserve(bytesize)) return CUDA_ERROR_OUT_OF_MEMORY;  // the driver is not called (hook.cpp:995)
   CUresult r = GH_REAL_CORE(cuMemAlloc_v2)(dptr, bytesize);
   if (r != CUDA_SUCCESS) {
@@ -95,12 +133,24 @@ GH_HOOK cuMemAlloc_v2(CUdeviceptr* dptr, size_t bytesize) {
 }
 
 GH_HOOK cuMemAllocManaged(CUdeviceptr* dptr, size_t bytesize, unsigned int flags) {
-  gh_live_get();  // managed memory is not accounted (hook.cpp:619-627)
-  return GH_REAL_CORE(cuMemAllocManaged)(dptr, bytesize, flags);
+  GH_COUNT(cuMemAllocManaged);
+  gh_live_get();
+  // managed memory is not accounted by the reference (hook.cpp:619-627: empty pre/post hooks) -- kept as the default;
+  // GEMHOOK_ACCOUNT_MANAGED=1 charges it like cuMemAlloc
+  if (!gh_cfg.account_managed) return GH_REAL_CORE(cuMemAllocManaged)(dptr, bytesize, flags);
+  if (!gh_mem_reserve(bytesize)) return CUDA_ERROR_OUT_OF_MEMORY;
+  CUresult r = GH_REAL_CORE(cuMemAllocManaged)(dptr, bytesize, flags);
+  if (r != CUDA_SUCCESS) {
+    gh_mem_unreserve(bytesize);
+    return r;
+  }
+  gh_mem_commit((uint64_t)*dptr, bytesize);
+  return r;
 }
 
 GH_HOOK cuMemAllocPitch_v2(CUdeviceptr* dptr, size_t* pPitch, size_t WidthInBytes, size_t Height,
                            unsigned int ElementSizeBytes) {
+  GH_COUNT(cuMemAllocPitch);
   // the charge is pitch * Height with the REAL pitch (reference post-hook, hook.cpp:633-636; its pre-hook
   // reads *pPitch before the driver wrote it, :629-632).  The pitch is only known after the call, so the
   // reservation follows it and a denied reservation frees the allocation again.
@@ -117,11 +167,13 @@ GH_HOOK cuMemAllocPitch_v2(CUdeviceptr* dptr, size_t* pPitch, size_t WidthInByte
 }
 
 GH_HOOK cuMemFree_v2(CUdeviceptr dptr) {
+  GH_COUNT(cuMemFree);
   gh_mem_free_key((uint64_t)dptr);
   return GH_REAL_CORE(cuMemFree_v2)(dptr);
 }
 
 GH_HOOK cuArrayCreate_v2(CUarray* pHandle, const CUDA_ARRAY_DESCRIPTOR* d) {
+  GH_COUNT(cuArrayCreate);
   uint64_t bytes = gemhook_array_bytes(d->Width, d->Height, 0, d->NumChannels, (uint32_t)d->Format, 0);
   if (!gh_mem_reserve(bytes)) return CUDA_ERROR_OUT_OF_MEMORY;
   CUresult r = GH_REAL_CORE(cuArrayCreate_v2)(pHandle, d);
@@ -134,6 +186,7 @@ GH_HOOK cuArrayCreate_v2(CUarray* pHandle, const CUDA_ARRAY_DESCRIPTOR* d) {
 }
 
 GH_HOOK cuArray3DCreate_v2(CUarray* pHandle, const CUDA_ARRAY3D_DESCRIPTOR* d) {
+  GH_COUNT(cuArray3DCreate);
   uint64_t bytes = gemhook_array_bytes(d->Width, d->Height, d->Depth, d->NumChannels, (uint32_t)d->Format, 1);
   if (!gh_mem_reserve(bytes)) return CUDA_ERROR_OUT_OF_MEMORY;
   CUresult r = GH_REAL_CORE(cuArray3DCreate_v2)(pHandle, d);
@@ -146,16 +199,30 @@ GH_HOOK cuArray3DCreate_v2(CUarray* pHandle, const CUDA_ARRAY3D_DESCRIPTOR* d) {
 }
 
 GH_HOOK cuMipmappedArrayCreate(CUmipmappedArray* pHandle, const CUDA_ARRAY3D_DESCRIPTOR* d, unsigned int levels) {
-  gh_live_get();  // not accounted (hook.cpp:682-694)
-  return GH_REAL_CORE(cuMipmappedArrayCreate)(pHandle, d, levels);
+  GH_COUNT(cuMipmappedArrayCreate);
+  gh_live_get();
+  // not accounted by the reference (hook.cpp:682-694); with GEMHOOK_ACCOUNT_MANAGED=1 every level is charged with
+  // the array rule of hook.cpp:668-680, each extent halving (floor, at least 1) per level
+  if (!gh_cfg.account_managed || !d) return GH_REAL_CORE(cuMipmappedArrayCreate)(pHandle, d, levels);
+  uint64_t bytes = gemhook_mipmap_bytes(d->Width, d->Height, d->Depth, d->NumChannels, (uint32_t)d->Format, levels);
+  if (!gh_mem_reserve(bytes)) return CUDA_ERROR_OUT_OF_MEMORY;
+  CUresult r = GH_REAL_CORE(cuMipmappedArrayCreate)(pHandle, d, levels);
+  if (r != CUDA_SUCCESS) {
+    gh_mem_unreserve(bytes);
+    return r;
+  }
+  gh_mem_commit((uint64_t)(uintptr_t)*pHandle, bytes);
+  return r;
 }
 
 GH_HOOK cuArrayDestroy(CUarray hArray) {
+  GH_COUNT(cuArrayDestroy);
   gh_mem_free_key((uint64_t)(uintptr_t)hArray);
   return GH_REAL_CORE(cuArrayDestroy)(hArray);
 }
 
 GH_HOOK cuMipmappedArrayDestroy(CUmipmappedArray h) {
+  GH_COUNT(cuMipmappedArrayDestroy);
   gh_mem_free_key((uint64_t)(uintptr_t)h);
   return GH_REAL_CORE(cuMipmappedArrayDestroy)(h);
 }
@@ -163,6 +230,7 @@ GH_HOOK cuMipmappedArrayDestroy(CUmipmappedArray h) {
 // mem-info virtualisation: the driver is never asked (hook.cpp:857-872)
 extern "C" int gh_live_enabled(void);
 GH_HOOK cuMemGetInfo_v2(size_t* free_b, size_t* total_b) {
+  GH_COUNT(cuMemGetInfo);
   if (!gh_live_get() || !gh_live_enabled()) return GH_REAL_CORE(cuMemGetInfo_v2)(free_b, total_b);
   uint64_t f = 0, t = 0;
   gh_mem_info(&f, &t);
@@ -171,6 +239,7 @@ GH_HOOK cuMemGetInfo_v2(size_t* free_b, size_t* total_b) {
   return CUDA_SUCCESS;
 }
 GH_HOOK cuDeviceTotalMem_v2(size_t* bytes, CUdevice dev) {
+  GH_COUNT(cuDeviceTotalMem);
   if (!gh_live_get() || !gh_live_enabled()) return GH_REAL_CORE(cuDeviceTotalMem_v2)(bytes, dev);
   uint64_t f = 0, t = 0;
   gh_mem_info(&f, &t);
@@ -180,14 +249,16 @@ GH_HOOK cuDeviceTotalMem_v2(size_t* bytes, CUdevice dev) {
 
 // ---- synchronising calls: burst end / window start (hook.cpp:696-722) -------------------------------------
 GH_HOOK cuCtxSynchronize(void) {
+  GH_COUNT(cuCtxSynchronize);
   gh_host_sync_pre();
   CUresult r = GH_REAL_CORE(cuCtxSynchronize)();
   if (r == CUDA_SUCCESS) gh_host_sync_post();
   return r;
 }
 
-#define GH_SYNC_COPY(export_name, real_expr, params, args) \
+#define GH_SYNC_COPY(counter, export_name, real_expr, params, args) \
   GH_HOOK export_name params {                             \
+    if (__builtin_expect(__atomic_load_n(&gh_hook_debug, __ATOMIC_RELAXED), 0)) __atomic_add_fetch(&g_calls[counter], 1, __ATOMIC_RELAXED); \
     gh_host_sync_pre();                                    \
     CUresult r = (real_expr)args;                          \
     if (r == CUDA_SUCCESS) gh_host_sync_post();            \
@@ -200,14 +271,14 @@ typedef CUresult(CUDAAPI* htoa_fn)(CUarray, size_t, const void*, size_t);
 typedef CUresult(CUDAAPI* htod_fn)(CUdeviceptr, const void*, size_t);
 static void *p_atoh_ptds, *p_dtoh_ptds, *p_htoa_ptds, *p_htod_ptds;
 
-GH_SYNC_COPY(cuMemcpyAtoH_v2, GH_REAL_CORE(cuMemcpyAtoH_v2), (void* dst, CUarray src, size_t off, size_t n), (dst, src, off, n))
-GH_SYNC_COPY(cuMemcpyDtoH_v2, GH_REAL_CORE(cuMemcpyDtoH_v2), (void* dst, CUdeviceptr src, size_t n), (dst, src, n))
-GH_SYNC_COPY(cuMemcpyHtoA_v2, GH_REAL_CORE(cuMemcpyHtoA_v2), (CUarray dst, size_t off, const void* src, size_t n), (dst, off, src, n))
-GH_SYNC_COPY(cuMemcpyHtoD_v2, GH_REAL_CORE(cuMemcpyHtoD_v2), (CUdeviceptr dst, const void* src, size_t n), (dst, src, n))
-GH_SYNC_COPY(cuMemcpyAtoH_v2_ptds, (atoh_fn)LATE(p_atoh_ptds, "cuMemcpyAtoH_v2_ptds"), (void* dst, CUarray src, size_t off, size_t n), (dst, src, off, n))
-GH_SYNC_COPY(cuMemcpyDtoH_v2_ptds, (dtoh_fn)LATE(p_dtoh_ptds, "cuMemcpyDtoH_v2_ptds"), (void* dst, CUdeviceptr src, size_t n), (dst, src, n))
-GH_SYNC_COPY(cuMemcpyHtoA_v2_ptds, (htoa_fn)LATE(p_htoa_ptds, "cuMemcpyHtoA_v2_ptds"), (CUarray dst, size_t off, const void* src, size_t n), (dst, off, src, n))
-GH_SYNC_COPY(cuMemcpyHtoD_v2_ptds, (htod_fn)LATE(p_htod_ptds, "cuMemcpyHtoD_v2_ptds"), (CUdeviceptr dst, const void* src, size_t n), (dst, src, n))
+GH_SYNC_COPY(CNT_cuMemcpyAtoH, cuMemcpyAtoH_v2, GH_REAL_CORE(cuMemcpyAtoH_v2), (void* dst, CUarray src, size_t off, size_t n), (dst, src, off, n))
+GH_SYNC_COPY(CNT_cuMemcpyDtoH, cuMemcpyDtoH_v2, GH_REAL_CORE(cuMemcpyDtoH_v2), (void* dst, CUdeviceptr src, size_t n), (dst, src, n))
+GH_SYNC_COPY(CNT_cuMemcpyHtoA, cuMemcpyHtoA_v2, GH_REAL_CORE(cuMemcpyHtoA_v2), (CUarray dst, size_t off, const void* src, size_t n), (dst, off, src, n))
+GH_SYNC_COPY(CNT_cuMemcpyHtoD, cuMemcpyHtoD_v2, GH_REAL_CORE(cuMemcpyHtoD_v2), (CUdeviceptr dst, const void* src, size_t n), (dst, src, n))
+GH_SYNC_COPY(CNT_cuMemcpyAtoH, cuMemcpyAtoH_v2_ptds, (atoh_fn)LATE(p_atoh_ptds, "cuMemcpyAtoH_v2_ptds"), (void* dst, CUarray src, size_t off, size_t n), (dst, src, off, n))
+GH_SYNC_COPY(CNT_cuMemcpyDtoH, cuMemcpyDtoH_v2_ptds, (dtoh_fn)LATE(p_dtoh_ptds, "cuMemcpyDtoH_v2_ptds"), (void* dst, CUdeviceptr src, size_t n), (dst, src, n))
+GH_SYNC_COPY(CNT_cuMemcpyHtoA, cuMemcpyHtoA_v2_ptds, (htoa_fn)LATE(p_htoa_ptds, "cuMemcpyHtoA_v2_ptds"), (CUarray dst, size_t off, const void* src, size_t n), (dst, off, src, n))
+GH_SYNC_COPY(CNT_cuMemcpyHtoD, cuMemcpyHtoD_v2_ptds, (htod_fn)LATE(p_htod_ptds, "cuMemcpyHtoD_v2_ptds"), (CUdeviceptr dst, const void* src, size_t n), (dst, src, n))
 
 // ---- modern entry points the reference never saw ------------------------------------------
 // Stream-ordered allocations are charged like cuMemAlloc; graph launches pass the token gate like a kernel
@@ -224,6 +295,7 @@ static void *p_graphlaunch, *p_graphlaunch_pt, *p_streamsync, *p_streamsync_pt, 
 
 #define GH_ALLOC_ASYNC(name, slot, sym)                                        \
   GH_HOOK name(CUdeviceptr* dptr, size_t bytesize, CUstream hStream) {         \
+    GH_COUNT(cuMemAllocAsync);                                                 \
     if (!gh_mem_reserve(bytesize)) return CUDA_ERROR_OUT_OF_MEMORY;            \
     CUresult r = ((allocasync_fn)LATE(slot, sym))(dptr, bytesize, hStream);    \
     if (r != CUDA_SUCCESS) {                                                   \
@@ -238,6 +310,7 @@ GH_ALLOC_ASYNC(cuMemAllocAsync_ptsz, p_allocasync_pt, "cuMemAllocAsync_ptsz")
 
 #define GH_ALLOC_POOL(name, slot, sym)                                                  \
   GH_HOOK name(CUdeviceptr* dptr, size_t bytesize, CUmemoryPool pool, CUstream hStream) { \
+    GH_COUNT(cuMemAllocFromPoolAsync);                                                  \
     if (!gh_mem_reserve(bytesize)) return CUDA_ERROR_OUT_OF_MEMORY;                     \
     CUresult r = ((allocpool_fn)LATE(slot, sym))(dptr, bytesize, pool, hStream);        \
     if (r != CUDA_SUCCESS) {                                                            \
@@ -251,18 +324,22 @@ GH_ALLOC_POOL(cuMemAllocFromPoolAsync, p_allocpool, "cuMemAllocFromPoolAsync")
 GH_ALLOC_POOL(cuMemAllocFromPoolAsync_ptsz, p_allocpool_pt, "cuMemAllocFromPoolAsync_ptsz")
 
 GH_HOOK cuMemFreeAsync(CUdeviceptr dptr, CUstream hStream) {
+  GH_COUNT(cuMemFreeAsync);
   gh_mem_free_key((uint64_t)dptr);
   return ((freeasync_fn)LATE(p_freeasync, "cuMemFreeAsync"))(dptr, hStream);
 }
 GH_HOOK cuMemFreeAsync_ptsz(CUdeviceptr dptr, CUstream hStream) {
+  GH_COUNT(cuMemFreeAsync);
   gh_mem_free_key((uint64_t)dptr);
   return ((freeasync_fn)LATE(p_freeasync_pt, "cuMemFreeAsync_ptsz"))(dptr, hStream);
 }
 GH_HOOK cuGraphLaunch(CUgraphExec g, CUstream hStream) {
+  GH_COUNT(cuGraphLaunch);
   launch_gate(hStream);
   return ((graphlaunch_fn)LATE(p_graphlaunch, "cuGraphLaunch"))(g, hStream);
 }
 GH_HOOK cuGraphLaunch_ptsz(CUgraphExec g, CUstream hStream) {
+  GH_COUNT(cuGraphLaunch);
   launch_gate(hStream);
   return ((graphlaunch_fn)LATE(p_graphlaunch_pt, "cuGraphLaunch_ptsz"))(g, hStream);
 }
@@ -273,6 +350,7 @@ typedef CUresult(CUDAAPI* memrelease_fn)(CUmemGenericAllocationHandle);
 static void *p_memcreate, *p_memrelease;
 static inline uint64_t handle_key(CUmemGenericAllocationHandle h) { return (uint64_t)h ^ 0x8000000000000000ULL; }
 GH_HOOK cuMemCreate(CUmemGenericAllocationHandle* handle, size_t size, const CUmemAllocationProp* prop, unsigned long long flags) {
+  GH_COUNT(cuMemCreate);
   bool device = !prop || prop->location.type == CU_MEM_LOCATION_TYPE_DEVICE;
   if (device && !gh_mem_reserve(size)) return CUDA_ERROR_OUT_OF_MEMORY;
   CUresult r = ((memcreate_fn)LATE(p_memcreate, "cuMemCreate"))(handle, size, prop, flags);
@@ -285,12 +363,14 @@ GH_HOOK cuMemCreate(CUmemGenericAllocationHandle* handle, size_t size, const CUm
   return r;
 }
 GH_HOOK cuMemRelease(CUmemGenericAllocationHandle handle) {
+  GH_COUNT(cuMemRelease);
   gh_mem_free_key(handle_key(handle));
   return ((memrelease_fn)LATE(p_memrelease, "cuMemRelease"))(handle);
 }
 
 static inline bool extra_syncs(void) { return gh_live_get() && gh_cfg.extra_hooks; }
 GH_HOOK cuStreamSynchronize(CUstream hStream) {
+  GH_COUNT(cuStreamSynchronize);
   bool x = extra_syncs();
   if (x) gh_host_sync_pre();
   CUresult r = ((streamsync_fn)LATE(p_streamsync, "cuStreamSynchronize"))(hStream);
@@ -298,6 +378,7 @@ GH_HOOK cuStreamSynchronize(CUstream hStream) {
   return r;
 }
 GH_HOOK cuStreamSynchronize_ptsz(CUstream hStream) {
+  GH_COUNT(cuStreamSynchronize);
   bool x = extra_syncs();
   if (x) gh_host_sync_pre();
   CUresult r = ((streamsync_fn)LATE(p_streamsync_pt, "cuStreamSynchronize_ptsz"))(hStream);
@@ -305,11 +386,58 @@ GH_HOOK cuStreamSynchronize_ptsz(CUstream hStream) {
   return r;
 }
 GH_HOOK cuEventSynchronize(CUevent ev) {
+  GH_COUNT(cuEventSynchronize);
   bool x = extra_syncs();
   if (x) gh_host_sync_pre();
   CUresult r = ((eventsync_fn)LATE(p_eventsync, "cuEventSynchronize"))(ev);
   if (x && r == CUDA_SUCCESS) gh_host_sync_post();
   return r;
+}
+
+// cuStreamDestroy: a segment still open on the dying stream gets its end marker first (gh_hook.cpp)
+typedef CUresult(CUDAAPI* streamdestroy_fn)(CUstream);
+GH_HOOK cuStreamDestroy_v2(CUstream hStream) {
+  GH_COUNT(cuStreamDestroy);
+  if (gh_live_get()) gh_stream_destroyed(hStream);
+  return GH_REAL_CORE(cuStreamDestroy_v2)(hStream);
+}
+
+// Pinned host memory is not device memory and the reference does not see it at all; GEMHOOK_ACCOUNT_HOST=1 charges
+// it against gpu_mem anyway (a pod that pins host RAM takes it from every tenant of the node).  Off by default.
+typedef CUresult(CUDAAPI* allochost_fn)(void**, size_t);
+typedef CUresult(CUDAAPI* hostalloc_fn)(void**, size_t, unsigned int);
+typedef CUresult(CUDAAPI* freehost_fn)(void*);
+static inline uint64_t host_key(void* p) { return (uint64_t)(uintptr_t)p ^ 0x4000000000000000ULL; }
+GH_HOOK cuMemAllocHost_v2(void** pp, size_t bytesize) {
+  GH_COUNT(cuMemAllocHost);
+  bool charge = gh_live_get() && gh_cfg.account_host;
+  if (charge && !gh_mem_reserve(bytesize)) return CUDA_ERROR_OUT_OF_MEMORY;
+  CUresult r = GH_REAL_CORE(cuMemAllocHost_v2)(pp, bytesize);
+  if (!charge) return r;
+  if (r != CUDA_SUCCESS) {
+    gh_mem_unreserve(bytesize);
+    return r;
+  }
+  gh_mem_commit(host_key(*pp), bytesize);
+  return r;
+}
+GH_HOOK cuMemHostAlloc(void** pp, size_t bytesize, unsigned int flags) {
+  GH_COUNT(cuMemHostAlloc);
+  bool charge = gh_live_get() && gh_cfg.account_host;
+  if (charge && !gh_mem_reserve(bytesize)) return CUDA_ERROR_OUT_OF_MEMORY;
+  CUresult r = GH_REAL_CORE(cuMemHostAlloc)(pp, bytesize, flags);
+  if (!charge) return r;
+  if (r != CUDA_SUCCESS) {
+    gh_mem_unreserve(bytesize);
+    return r;
+  }
+  gh_mem_commit(host_key(*pp), bytesize);
+  return r;
+}
+GH_HOOK cuMemFreeHost(void* p) {
+  GH_COUNT(cuMemFreeHost);
+  if (gh_live_get() && gh_cfg.account_host) gh_mem_free_key(host_key(p));
+  return GH_REAL_CORE(cuMemFreeHost)(p);
 }
 
 // ---- symbol tables ---------------------------------------------------------------------------------------
@@ -353,6 +481,10 @@ static const HookEntry kHooks[] = {
     {"cuMemRelease", "cuMemRelease", (void*)&cuMemRelease, nullptr},
     {"cuStreamSynchronize", "cuStreamSynchronize", (void*)&cuStreamSynchronize, (void*)&cuStreamSynchronize_ptsz},
     {"cuEventSynchronize", "cuEventSynchronize", (void*)&cuEventSynchronize, nullptr},
+    {"cuStreamDestroy_v2", "cuStreamDestroy", (void*)&cuStreamDestroy_v2, nullptr},
+    {"cuMemAllocHost_v2", "cuMemAllocHost", (void*)&cuMemAllocHost_v2, nullptr},
+    {"cuMemHostAlloc", "cuMemHostAlloc", (void*)&cuMemHostAlloc, nullptr},
+    {"cuMemFreeHost", "cuMemFreeHost", (void*)&cuMemFreeHost, nullptr},
 };
 static const size_t kNumHooks = sizeof(kHooks) / sizeof(kHooks[0]);
 
@@ -363,7 +495,7 @@ static const char* const kHookedNames[] = {
     "cuMipmappedArrayDestroy", "cuMemGetInfo_v2", "cuDeviceTotalMem_v2", "cuCtxSynchronize",
     "cuMemcpyAtoH_v2", "cuMemcpyDtoH_v2", "cuMemcpyHtoA_v2", "cuMemcpyHtoD_v2",
     "cuMemAllocAsync", "cuMemAllocFromPoolAsync", "cuMemFreeAsync", "cuGraphLaunch", "cuMemCreate", "cuMemRelease", "cuStreamSynchronize",
-    "cuEventSynchronize", nullptr};
+    "cuEventSynchronize", "cuStreamDestroy_v2", "cuMemAllocHost_v2", "cuMemHostAlloc", "cuMemFreeHost", nullptr};
 
 extern "C" __attribute__((visibility("default"))) const char* const* gemhook_hooked_symbols(size_t* count) {
   if (count) *count = sizeof(kHookedNames) / sizeof(kHookedNames[0]) - 1;
@@ -377,6 +509,7 @@ extern "C" __attribute__((visibility("default"))) const char* const* gemhook_hoo
 // 158), which re-anchors RTLD_NEXT at the hook library.
 __attribute__((no_sanitize("thread", "address", "undefined"))) void* dlsym(void* handle, const char* symbol) {
   if (symbol && symbol[0] == 'c' && symbol[1] == 'u') {
+    GH_COUNT(dlsym);
     if (!strcmp(symbol, "cuGetProcAddress_v2")) return (void*)&cuGetProcAddress_v2;
     if (!strcmp(symbol, "cuGetProcAddress")) return (void*)&cuGetProcAddress;
     for (size_t i = 0; i < kNumHooks; i++)
@@ -419,6 +552,7 @@ static void swap_in_hook(const char* symbol, void** pfn, int cudaVersion, cuuint
 GH_HOOK cuGetProcAddress_v2(const char* symbol, void** pfn, int cudaVersion, cuuint64_t flags,
                             CUdriverProcAddressQueryResult* status) {
   typedef CUresult(CUDAAPI * fn_t)(const char*, void**, int, cuuint64_t, CUdriverProcAddressQueryResult*);
+  GH_COUNT(cuGetProcAddress);
   if (gh_driver_init() != 0 || !gh_real.gpa_v2) return CUDA_ERROR_NOT_INITIALIZED;
   CUresult r = ((fn_t)gh_real.gpa_v2)(symbol, pfn, cudaVersion, flags, status);
   if (r == CUDA_SUCCESS) swap_in_hook(symbol, pfn, cudaVersion, flags);
@@ -427,6 +561,7 @@ GH_HOOK cuGetProcAddress_v2(const char* symbol, void** pfn, int cudaVersion, cuu
 
 GH_HOOK cuGetProcAddress(const char* symbol, void** pfn, int cudaVersion, cuuint64_t flags) {
   typedef CUresult(CUDAAPI * fn_t)(const char*, void**, int, cuuint64_t);
+  GH_COUNT(cuGetProcAddress);
   if (gh_driver_init() != 0 || !gh_real.gpa_legacy) return CUDA_ERROR_NOT_INITIALIZED;
   CUresult r = ((fn_t)gh_real.gpa_legacy)(symbol, pfn, cudaVersion, flags);
   if (r == CUDA_SUCCESS) swap_in_hook(symbol, pfn, cudaVersion, flags);

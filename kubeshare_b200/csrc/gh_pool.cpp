@@ -603,11 +603,16 @@ static double pod_granted_locked(gemhook_pool* p, int slot, int64_t now_us, doub
 
 // Live acquisition: post the request, then arbitrate/wait until OUR slot is granted.
 GH_EXPORT double gemhook_pool_acquire(gemhook_pool* p, int slot, double overuse_ms, double burst_ms) {
+  return gemhook_pool_acquire_ex(p, slot, overuse_ms, burst_ms, nullptr);
+}
+GH_EXPORT double gemhook_pool_acquire_ex(gemhook_pool* p, int slot, double overuse_ms, double burst_ms, int* forwarded) {
   Slot& me = p->r->slots[slot];
+  if (forwarded) *forwarded = 1;
   p->lock();
   double fo = overuse_ms, fb = burst_ms, remain = 0.0;
   if (!pod_launch_locked(p, slot, p->attach_idx, p->now_us(), overuse_ms, burst_ms, &fo, &fb, &remain)) {
     p->unlock();
+    if (forwarded) *forwarded = 0;
     return remain;  // the pod's token still covers this burst (pod-manager.cpp:472)
   }
   request_locked(p, slot, p->now_ms(), fo, fb);
@@ -635,6 +640,7 @@ GH_EXPORT double gemhook_pool_acquire(gemhook_pool* p, int slot, double overuse_
       p->lock();
       if (!pod_launch_locked(p, slot, p->attach_idx, p->now_us(), overuse_ms, burst_ms, &fo, &fb, &remain)) {
         p->unlock();
+        if (forwarded) *forwarded = 0;
         return remain;
       }
       request_locked(p, slot, p->now_ms(), fo, fb);
@@ -848,9 +854,9 @@ GH_EXPORT int gemhook_pool_slot_info(const gemhook_pool* cp, int slot, gemhook_s
   return 0;
 }
 
-void gh_pool_publish_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches) {
-  p->r->slots[slot].gpu_ns.store(gpu_ns, std::memory_order_relaxed);
-  p->r->slots[slot].launches.store(launches, std::memory_order_relaxed);
+void gh_pool_add_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches) {
+  p->r->slots[slot].gpu_ns.fetch_add(gpu_ns, std::memory_order_relaxed);
+  p->r->slots[slot].launches.fetch_add(launches, std::memory_order_relaxed);
 }
 
 // hook.cpp:638-680: bytes charged for arrays.  CUarray_format: U8 0x01, U16 0x02, U32 0x03, S8 0x08,
@@ -865,4 +871,15 @@ GH_EXPORT uint64_t gemhook_array_bytes(uint64_t w, uint64_t h, uint64_t d, uint3
     default: fs = 0; break;
   }
   return (is3d ? w * h * d * channels : w * h * channels) * fs;
+}
+
+// Opt-in rule for mipmapped arrays (GEMHOOK_ACCOUNT_MANAGED=1; the reference charges nothing, hook.cpp:682-694): the
+// array rule above applied to every level, extents halving (floor, at least 1) from one level to the next.
+GH_EXPORT uint64_t gemhook_mipmap_bytes(uint64_t w, uint64_t h, uint64_t d, uint32_t channels, uint32_t format, uint32_t levels) {
+  uint64_t total = 0;
+  for (uint32_t l = 0; l < levels; l++) {
+    uint64_t lw = w >> l ? w >> l : 1, lh = h ? (h >> l ? h >> l : 1) : 0, ld = d ? (d >> l ? d >> l : 1) : 0;
+    total += gemhook_array_bytes(lw, lh ? lh : 1, ld ? ld : 1, channels, format, 1);
+  }
+  return total;
 }

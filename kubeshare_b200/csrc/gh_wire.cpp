@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <unistd.h>
 
 #include "gh_internal.h"
@@ -178,6 +179,10 @@ static int rpc_connect(void) {
 }
 
 // One request/response exchange. Returns 0 and fills rsp, or -1 (caller decides whether to exit()).
+// Retry policy of the reference's communicate() (hook.cpp:300-328 with comm.cpp:124-134): the receive timeout is set
+// per call (10 s for the memory requests, none for a token request, hook.cpp:357, 385, 437), and a failed send or
+// receive is retried -- send AND receive again, on the same socket -- up to NET_OP_MAX_ATTEMPT = 5 times before the
+// exchange is declared failed.
 int gh_rpc(gemhook_request* req, gemhook_response* rsp) {
   uint8_t sbuf[GEMHOOK_REQ_LEN], rbuf[GEMHOOK_RSP_LEN];
   pthread_mutex_lock(&rpc_mu);
@@ -186,11 +191,22 @@ int gh_rpc(gemhook_request* req, gemhook_response* rsp) {
   if (rpc_fd >= 0) {
     snprintf(req->name, sizeof(req->name), "%s", gh_cfg.pod_name);
     req->req_id = rpc_next_id++;
-    if (gemhook_wire_pack_request(req, sbuf) > 0 && full_send(rpc_fd, sbuf, sizeof(sbuf)) == 0 &&
-        full_recv(rpc_fd, rbuf, sizeof(rbuf)) == 0) {
-      gemhook_wire_unpack_response(req->type, rbuf, rsp);
-      rc = 0;
-    } else {
+    if (gemhook_wire_pack_request(req, sbuf) > 0) {
+      struct timeval tv;
+      static int mem_timeout_s = getenv("GEMHOOK_RPC_TIMEOUT_S") ? atoi(getenv("GEMHOOK_RPC_TIMEOUT_S")) : 10;  // NET_OP_RETRY_INTV
+      tv.tv_sec = req->type == GEMHOOK_REQ_QUOTA ? 0 : mem_timeout_s;
+      tv.tv_usec = 0;
+      setsockopt(rpc_fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+      for (int attempt = 1; attempt <= 5 && rc != 0; attempt++) {
+        if (full_send(rpc_fd, sbuf, sizeof(sbuf)) == 0 && full_recv(rpc_fd, rbuf, sizeof(rbuf)) == 0) {
+          gemhook_wire_unpack_response(req->type, rbuf, rsp);
+          rc = 0;
+        } else {
+          GH_INFO("token protocol exchange failed (attempt %d): %s", attempt, strerror(errno));
+        }
+      }
+    }
+    if (rc != 0) {
       gh_set_error("token protocol exchange failed: %s", strerror(errno));
       close(rpc_fd);
       rpc_fd = -1;

@@ -3,6 +3,8 @@
  *   gem-poolctl POOL dump            JSON: one object per client
  *   gem-poolctl POOL prom            Prometheus text exposition (gauge names mirror kubeshare-aggregator's
  *                                    gpu_requirement labels: reference pkg/aggregator/aggregator.go:22-38)
+ *   gem-poolctl POOL ledger          the token ledger in the shape gem-schd's _DEBUG build dumps on SIGINT
+ *                                    (reference scheduler.cpp:693-714): [{"container", "start", "end"}] in seconds
  *   gem-poolctl POOL load FILE [limit_request]   (re)load a quota file into the pool
  *   gem-poolctl POOL reap            reclaim bytes / token of dead clients
  */
@@ -14,7 +16,7 @@
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    fprintf(stderr, "usage: gem-poolctl POOL dump|prom|load FILE [limit_request]|reap\n");
+    fprintf(stderr, "usage: gem-poolctl POOL dump|prom|ledger|load FILE [limit_request]|reap\n");
     return 2;
   }
   gemhook_pool* p = gemhook_pool_open(argv[1], !strcmp(argv[2], "load"), 300.0, 20.0, 10000.0, 0);
@@ -48,6 +50,22 @@ int main(int argc, char** argv) {
              (unsigned long long)s.mem_used);
       printf("gemhook_mem_limit_bytes{pod=\"%s\"} %llu\n", s.name, (unsigned long long)s.mem_limit);
     }
+  } else if (!strcmp(argv[2], "ledger")) {
+    size_t k = gemhook_pool_history(p, NULL, NULL, NULL, 0);
+    int* sl = (int*)calloc(k + 1, sizeof(int));
+    double* a = (double*)calloc(k + 1, sizeof(double));
+    double* b = (double*)calloc(k + 1, sizeof(double));
+    size_t got = gemhook_pool_history(p, sl, a, b, k);
+    if (got < k) k = got;
+    printf("[\n");
+    for (size_t i = 0; i < k; i++) {
+      gemhook_pool_slot_info(p, sl[i], &s);
+      printf("\t{\"container\": \"%s\", \"start\": %.3lf, \"end\" : %.3lf}%s\n", s.name, a[i] / 1000.0, b[i] / 1000.0, i + 1 < k ? "," : "");
+    }
+    printf("]\n");
+    free(sl);
+    free(a);
+    free(b);
   } else if (!strcmp(argv[2], "load") && argc >= 4) {
     FILE* f = fopen(argv[3], "r");
     if (!f) {

@@ -10,6 +10,9 @@
  *   memsweep cudaMalloc-style sweep: 256 MiB x i cumulative toward --sweep-bytes, then 1000 odd-sized
  *            allocations U[1, 64 MiB], seed 4                                           (config 4)
  *   mnist    iterations of 100 conv launches (N=64, 1->32->64 channels, 28x28, 3x3) + one DtoH (config 5)
+ *   truth    R bursts of L self-timing spin kernels (on 1 or 2 streams), sync, optional idle sleep; reports the sum
+ *            of the per-burst busy spans measured with %globaltimer INSIDE the kernels  (independent SM-time truth)
+ *   graph    capture a CUDA graph on a non-blocking stream while hooked, replay it        (capture safety)
  *   probe    host cost of the primitives the hook builds on (launch, event record, elapsed, stamp)
  *
  * Output: ONE JSON object on stdout (or --out FILE).  Timing: CUDA events around the timed region on the
@@ -74,7 +77,7 @@ static void barrier(const char* dir, int id, int n, const char* tag) {
   }
 }
 
-static CUfunction f_noop, f_spin, f_conv;
+static CUfunction f_noop, f_spin, f_conv, f_spin_stamp;
 
 /* multi-threaded client: every thread launches on its own stream and synchronises now and then */
 #include <pthread.h>
@@ -138,6 +141,7 @@ int main(int argc, char** argv) {
   CK(cuModuleGetFunction(&f_noop, mod, "noop"));
   CK(cuModuleGetFunction(&f_spin, mod, "spin"));
   CK(cuModuleGetFunction(&f_conv, mod, "conv3x3"));
+  CK(cuModuleGetFunction(&f_spin_stamp, mod, "spin_stamp"));
   CUevent e0, e1;
   CK(cuEventCreate(&e0, CU_EVENT_DEFAULT));
   CK(cuEventCreate(&e1, CU_EVENT_DEFAULT));
@@ -337,6 +341,29 @@ int main(int argc, char** argv) {
     cuMemGetInfo(&fr[5], &tot);
     fprintf(out, "{\"mode\": \"arrays\", \"rc\": [%d, %d, %d], \"pitch\": %zu, \"free\": [%zu, %zu, %zu, %zu, %zu, %zu], \"total\": %zu}\n",
             (int)r1, (int)r2, (int)r3, pitch, fr[0], fr[1], fr[2], fr[3], fr[4], fr[5], tot);
+  } else if (!strcmp(mode, "optin")) {
+    /* allocations the reference does not account (hook.cpp:619-627, 682-694) and pinned host memory: what is charged
+     * with GEMHOOK_ACCOUNT_MANAGED / GEMHOOK_ACCOUNT_HOST */
+    size_t fr[5] = {0}, tot = 0;
+    CUdeviceptr dm = 0;
+    CUmipmappedArray mm = NULL;
+    void* hp = NULL;
+    CUDA_ARRAY3D_DESCRIPTOR d3;
+    memset(&d3, 0, sizeof(d3));
+    d3.Width = 8; d3.Height = 8; d3.Depth = 0; d3.NumChannels = 1; d3.Format = CU_AD_FORMAT_FLOAT; /* 256 + 64 + 16 B over 3 levels */
+    cuMemGetInfo(&fr[0], &tot);
+    CUresult r1 = cuMemAllocManaged(&dm, 4096, CU_MEM_ATTACH_GLOBAL);
+    cuMemGetInfo(&fr[1], &tot);
+    CUresult r2 = cuMipmappedArrayCreate(&mm, &d3, 3);
+    cuMemGetInfo(&fr[2], &tot);
+    CUresult r3 = cuMemAllocHost(&hp, 2048);
+    cuMemGetInfo(&fr[3], &tot);
+    if (r3 == CUDA_SUCCESS) cuMemFreeHost(hp);
+    if (r2 == CUDA_SUCCESS) cuMipmappedArrayDestroy(mm);
+    if (r1 == CUDA_SUCCESS) cuMemFree(dm);
+    cuMemGetInfo(&fr[4], &tot);
+    fprintf(out, "{\"mode\": \"optin\", \"rc\": [%d, %d, %d], \"free\": [%zu, %zu, %zu, %zu, %zu], \"total\": %zu}\n", (int)r1, (int)r2,
+            (int)r3, fr[0], fr[1], fr[2], fr[3], fr[4], tot);
   } else if (!strcmp(mode, "mt")) {
     int T = nclients > 1 ? nclients : 4;  /* --nclients doubles as thread count here */
     pthread_t tid[64];
@@ -393,6 +420,75 @@ int main(int argc, char** argv) {
             (int)r1, (int)r2, (int)r3, fr, fr2, tot, gran, (int)v1, (int)v2, fr3, fr4);
     if (r1 == CUDA_SUCCESS) cuMemFreeAsync(a, st);
     CK(cuStreamSynchronize(st));
+  } else if (!strcmp(mode, "truth")) {
+    /* --rounds R bursts; --step-launches L kernels per burst; --spin-us; --sleep-mean-ms = FIXED idle after each sync
+     * (0 = relaunch at once); --nclients doubles as the number of streams (1 = legacy default stream, 2 = two
+     * non-blocking streams used alternately) */
+    int nstreams = nclients > 1 ? 2 : 0;
+    CUstream st[2] = {NULL, NULL};
+    for (int i = 0; i < nstreams; i++) CK(cuStreamCreate(&st[i], CU_STREAM_NON_BLOCKING));
+    CUdeviceptr d_bounds;
+    size_t bb = (size_t)rounds * 2 * sizeof(unsigned long long);
+    unsigned long long* h_bounds = (unsigned long long*)malloc(bb);
+    for (long r = 0; r < rounds; r++) {
+      h_bounds[2 * r] = ~0ULL;
+      h_bounds[2 * r + 1] = 0ULL;
+    }
+    CK(cuMemAlloc(&d_bounds, bb));
+    CK(cuMemcpyHtoD(d_bounds, h_bounds, bb));
+    unsigned long long ns = (unsigned long long)(spin_us * 1000.0);
+    double t0 = now_s();
+    for (long r = 0; r < rounds; r++) {
+      unsigned burst = (unsigned)r;
+      void* args[] = {&ns, &d_bounds, &burst};
+      for (long i = 0; i < step_launches; i++)
+        CK(cuLaunchKernel(f_spin_stamp, 1, 1, 1, 32, 1, 1, 0, nstreams ? st[i & 1] : NULL, args, NULL));
+      CK(cuCtxSynchronize());
+      if (sleep_mean_ms > 0) {
+        struct timespec ts = {(time_t)(sleep_mean_ms / 1e3), (long)(fmod(sleep_mean_ms, 1e3) * 1e6)};
+        nanosleep(&ts, NULL);
+      }
+    }
+    double t1 = now_s();
+    CK(cuMemcpyDtoH(h_bounds, d_bounds, bb));
+    unsigned long long truth = 0;
+    for (long r = 0; r < rounds; r++)
+      if (h_bounds[2 * r + 1] > h_bounds[2 * r]) truth += h_bounds[2 * r + 1] - h_bounds[2 * r];
+    fprintf(out, "{\"mode\": \"truth\", \"rounds\": %ld, \"launches\": %ld, \"streams\": %d, \"spin_us\": %.3f, "
+            "\"idle_ms\": %.3f, \"truth_ns\": %llu, \"wall_s\": %.9f}\n",
+            rounds, rounds * step_launches, nstreams ? 2 : 1, spin_us, sleep_mean_ms, truth, t1 - t0);
+  } else if (!strcmp(mode, "graph")) {
+    /* capture `step_launches` kernels into a graph on a non-blocking stream (short tokens may expire meanwhile),
+     * instantiate, replay `rounds` times; every API result is reported */
+    CUstream cs;
+    CK(cuStreamCreate(&cs, CU_STREAM_NON_BLOCKING));
+    for (int i = 0; i < 64; i++) CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, cs, NULL, NULL)); /* open a segment on cs */
+    CUgraph g = NULL;
+    CUgraphExec ge = NULL;
+    unsigned long long ns = (unsigned long long)(spin_us * 1000.0);
+    void* args[] = {&ns};
+    CUresult rb = cuStreamBeginCapture(cs, CU_STREAM_CAPTURE_MODE_GLOBAL);
+    CUresult rl = CUDA_SUCCESS;
+    for (long i = 0; i < step_launches && rl == CUDA_SUCCESS; i++) {
+      rl = cuLaunchKernel(f_spin, 1, 1, 1, 32, 1, 1, 0, cs, args, NULL);
+      if (i % 16 == 15) usleep(2000); /* let short tokens expire during the capture */
+    }
+    CUresult re = cuStreamEndCapture(cs, &g);
+    size_t nodes = 0;
+    if (re == CUDA_SUCCESS && g) cuGraphGetNodes(g, NULL, &nodes);
+    CUresult ri = (re == CUDA_SUCCESS && g) ? cuGraphInstantiateWithFlags(&ge, g, 0) : CUDA_ERROR_INVALID_VALUE;
+    CUresult rr = CUDA_SUCCESS;
+    for (long r = 0; r < rounds && ri == CUDA_SUCCESS && rr == CUDA_SUCCESS; r++) {
+      rr = cuGraphLaunch(ge, cs);
+      if (rr == CUDA_SUCCESS) rr = cuStreamSynchronize(cs);
+    }
+    CUresult rs = cuCtxSynchronize();
+    CUresult rd = cuStreamDestroy(cs);
+    for (int i = 0; i < 64; i++) CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+    CK(cuCtxSynchronize());
+    fprintf(out, "{\"mode\": \"graph\", \"begin\": %d, \"launch\": %d, \"end\": %d, \"nodes\": %zu, \"instantiate\": %d, "
+            "\"replay\": %d, \"sync\": %d, \"destroy\": %d, \"captured\": %ld, \"replays\": %ld}\n",
+            (int)rb, (int)rl, (int)re, nodes, (int)ri, (int)rr, (int)rs, (int)rd, step_launches, rounds);
   } else if (!strcmp(mode, "probe")) {
     /* host cost (ns) of the building blocks; medians would be nicer, means over 20k are stable enough */
     const int N = 20000;

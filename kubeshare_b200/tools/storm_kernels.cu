@@ -13,6 +13,21 @@ __global__ void spin(unsigned long long ns) {
   } while (t - t0 < ns);
 }
 
+// Independent truth for the accounting tests: the kernel spins for `ns` and folds its own %globaltimer start/end into
+// the bounds of its burst (bounds[2b] = earliest start, bounds[2b+1] = latest end), so the busy span of every burst is
+// known from the device's own clock without any event.
+__global__ void spin_stamp(unsigned long long ns, unsigned long long* __restrict__ bounds, unsigned burst) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+  if (threadIdx.x == 0) {
+    atomicMin(bounds + 2 * burst, t0);
+    atomicMax(bounds + 2 * burst + 1, t);
+  }
+}
+
 // out[n][co][y][x] = relu(sum_{ci,ky,kx} in[n][ci][y+ky-1][x+kx-1] * w[co][ci][ky][kx]); 28x28 images
 __global__ void conv3x3(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
                         int cin, int cout) {

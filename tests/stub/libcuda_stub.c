@@ -24,6 +24,7 @@
 static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
 static int64_t gpu_free_at_ns;  /* the timeline: when already-issued work completes */
 static uint64_t n_launch, n_coop, n_alloc, n_free, n_sync, n_event_record, n_memcpy, n_module, n_getproc;
+static uint64_t n_event_on_capturing, n_stream_destroy;
 static uint64_t bytes_live, next_addr = 0x700000000000ULL;
 static int fake_ctx_obj, fake_mod_obj;
 static __thread CUcontext cur_ctx;
@@ -73,11 +74,12 @@ static void report(void) {
   if (!f) return;
   fprintf(f,
           "{\"launches\": %llu, \"coop_launches\": %llu, \"allocs\": %llu, \"frees\": %llu, \"syncs\": %llu, "
-          "\"event_records\": %llu, \"memcpys\": %llu, \"modules\": %llu, \"getproc\": %llu, \"bytes_live\": %llu}\n",
+          "\"event_records\": %llu, \"memcpys\": %llu, \"modules\": %llu, \"getproc\": %llu, \"bytes_live\": %llu, "
+          "\"events_on_capturing_streams\": %llu, \"stream_destroys\": %llu}\n",
           (unsigned long long)n_launch, (unsigned long long)n_coop, (unsigned long long)n_alloc,
           (unsigned long long)n_free, (unsigned long long)n_sync, (unsigned long long)n_event_record,
           (unsigned long long)n_memcpy, (unsigned long long)n_module, (unsigned long long)n_getproc,
-          (unsigned long long)bytes_live);
+          (unsigned long long)bytes_live, (unsigned long long)n_event_on_capturing, (unsigned long long)n_stream_destroy);
   fclose(f);
 }
 
@@ -129,15 +131,30 @@ CUresult cuModuleGetFunction(CUfunction* f, CUmodule m, const char* name) {
 CUresult cuFuncSetAttribute(CUfunction f, CUfunction_attribute a, int v) { return CUDA_SUCCESS; }
 CUresult cuOccupancyMaxActiveBlocksPerMultiprocessor(int* n, CUfunction f, int bs, size_t smem) { *n = 2; return CUDA_SUCCESS; }
 
-CUresult cuStreamCreate(CUstream* s, unsigned int fl) { *s = (CUstream)malloc(8); return CUDA_SUCCESS; }
-CUresult cuStreamDestroy_v2(CUstream s) { free(s); return CUDA_SUCCESS; }
+CUresult cuStreamCreate(CUstream* s, unsigned int fl) { *s = (CUstream)calloc(1, 8); return CUDA_SUCCESS; }
+CUresult cuStreamDestroy_v2(CUstream s) { n_stream_destroy++; free(s); return CUDA_SUCCESS; }
 CUresult cuStreamSynchronize(CUstream s) { wait_until(timeline()); return CUDA_SUCCESS; }
+/* stream capture: a flag in the fake stream object; events recorded on a capturing stream are counted (the hook must
+ * keep its events off such a stream) */
+static int stub_capturing(CUstream s) { return s && *(int*)s; }
+CUresult cuStreamIsCapturing(CUstream s, CUstreamCaptureStatus* st) {
+  *st = stub_capturing(s) ? CU_STREAM_CAPTURE_STATUS_ACTIVE : CU_STREAM_CAPTURE_STATUS_NONE;
+  return CUDA_SUCCESS;
+}
+static int fake_graph_obj;
+CUresult cuStreamBeginCapture_v2(CUstream s, CUstreamCaptureMode m) { if (!s) return CUDA_ERROR_INVALID_VALUE; *(int*)s = 1; return CUDA_SUCCESS; }
+CUresult cuStreamEndCapture(CUstream s, CUgraph* g) { if (!s) return CUDA_ERROR_INVALID_VALUE; *(int*)s = 0; *g = (CUgraph)&fake_graph_obj; return CUDA_SUCCESS; }
+CUresult cuGraphGetNodes(CUgraph g, CUgraphNode* nodes, size_t* n) { *n = 0; return CUDA_SUCCESS; }
+CUresult cuGraphLaunch(CUgraphExec ge, CUstream s) { __atomic_add_fetch(&n_launch, 1, __ATOMIC_RELAXED); enqueue(kernel_ns()); return CUDA_SUCCESS; }
+CUresult cuGraphInstantiateWithFlags(CUgraphExec* ge, CUgraph g, unsigned long long fl) { *ge = (CUgraphExec)&fake_graph_obj; return CUDA_SUCCESS; }
+CUresult cuThreadExchangeStreamCaptureMode(CUstreamCaptureMode* m) { return CUDA_SUCCESS; }
 
 struct stub_event { int64_t t; int recorded; };
 CUresult cuEventCreate(CUevent* e, unsigned int fl) { *e = (CUevent)calloc(1, sizeof(struct stub_event)); return CUDA_SUCCESS; }
 CUresult cuEventDestroy_v2(CUevent e) { free(e); return CUDA_SUCCESS; }
 CUresult cuEventRecord(CUevent e, CUstream s) {
   n_event_record++;
+  if (stub_capturing(s)) n_event_on_capturing++;
   struct stub_event* ev = (struct stub_event*)e;
   ev->t = timeline();
   ev->recorded = 1;
@@ -190,6 +207,7 @@ CUresult cuMemFree_v2(CUdeviceptr p) {
 }
 CUresult cuMemHostAlloc(void** pp, size_t bytes, unsigned int fl) { *pp = calloc(1, bytes); return *pp ? CUDA_SUCCESS : CUDA_ERROR_OUT_OF_MEMORY; }
 CUresult cuMemFreeHost(void* p) { free(p); return CUDA_SUCCESS; }
+CUresult cuMemAllocHost_v2(void** pp, size_t bytes) { *pp = calloc(1, bytes); return *pp ? CUDA_SUCCESS : CUDA_ERROR_OUT_OF_MEMORY; }
 CUresult cuMemHostGetDevicePointer_v2(CUdeviceptr* d, void* p, unsigned int fl) { *d = (CUdeviceptr)(uintptr_t)p; return CUDA_SUCCESS; }
 CUresult cuMemHostRegister_v2(void* p, size_t bytes, unsigned int fl) { return CUDA_SUCCESS; }
 CUresult cuMemHostUnregister(void* p) { return CUDA_SUCCESS; }
@@ -210,6 +228,7 @@ CUresult cuMipmappedArrayDestroy(CUmipmappedArray h) { free(h); return CUDA_SUCC
 CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
                         unsigned sh, CUstream s, void** p, void** e) {
   __atomic_add_fetch(&n_launch, 1, __ATOMIC_RELAXED);
+  if (stub_capturing(s)) return CUDA_SUCCESS; /* captured, not executed */
   enqueue(kernel_ns());
   return CUDA_SUCCESS;
 }
