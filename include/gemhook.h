@@ -136,8 +136,10 @@ double gemhook_predictor_predict_merged(gemhook_predictor *, int64_t now_ns);
 /* ===================================================================================================
  * (2c) shared credit pool + token policy -- replaces hook->gem-pmgr->gem-schd TCP round trips
  *      (hook.cpp:300-328, 425-446; pod-manager.cpp:295-473; scheduler.cpp:123-174, 274-529).
- *      One file-backed MAP_SHARED region per GPU; every co-resident client maps it (and pins it with
- *      cuMemHostRegister so the device sees the same words).
+ *      One file-backed MAP_SHARED region per GPU; every co-resident client maps it (and pins its first pages with
+ *      cuMemHostRegister so the device sees the same counters).  LOCK-FREE: every mutation is a copy-on-write
+ *      transaction on a versioned state block published with one compare-and-swap; readers validate against the
+ *      version word; a client killed at any point blocks nobody (gh_pool.cpp).
  * =================================================================================================== */
 typedef struct gemhook_pool gemhook_pool;
 /* create=1: create/initialise if absent (node agent or first hook); scheduler parameters as gem-schd's
@@ -188,6 +190,9 @@ typedef struct gemhook_slot_info {
   int32_t holds_token, waiting;
 } gemhook_slot_info;
 int gemhook_pool_slot_info(const gemhook_pool *, int slot, gemhook_slot_info *out);
+/* transaction statistics of the lock-free pool: committed transactions, lost publication races (retried), state blocks
+ * recycled after their owner died or stalled. */
+void gemhook_pool_counters(const gemhook_pool *, uint64_t *commits, uint64_t *conflicts, uint64_t *recycled);
 
 /* process attachment: liveness is an OFD byte-range lock on the pool file, so bytes (and a held token) of a
  * process that died without cleaning up are reclaimed by gemhook_pool_reap() -- the reference does this on

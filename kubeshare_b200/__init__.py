@@ -96,6 +96,7 @@ def lib():
         "gemhook_pool_release": (None, [vp, C.c_int]),
         "gemhook_pool_expire_token": (None, [vp]), "gemhook_pool_others_waiting": (C.c_int, [vp, C.c_int]),
         "gemhook_pool_slot_info": (C.c_int, [vp, C.c_int, C.POINTER(SlotInfo)]),
+        "gemhook_pool_counters": (None, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "gemhook_pool_attach": (C.c_int, [vp, C.c_int]), "gemhook_pool_detach": (None, [vp]),
         "gemhook_pool_reap": (C.c_int, [vp]),
         "gemhook_pool_pod_launch": (C.c_int, [vp, C.c_int, i64, d, d, pd, pd, pd]),

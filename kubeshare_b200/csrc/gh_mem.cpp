@@ -171,6 +171,6 @@ void gh_mem_info(uint64_t* free_b, uint64_t* total_b) {
     if (gh_cfg.transport == 1) gemhook_pool_mem_info(gh_live_pool(), gh_live_slot(), &used, &total);
     else tcp_mem_limit(&used, &total);
   }
-  if (free_b) *free_b = total - used;
+  if (free_b) *free_b = used < total ? total - used : 0;  // (a reload may have lowered the limit below what is in use)
   if (total_b) *total_b = total;
 }

@@ -39,6 +39,10 @@
 #include "../../include/gemhook.h"
 
 static gemhook_pool* g_pool;
+// legacy connections per pool slot: processes of one pod share the pod's token (pod-manager.cpp:316-473), so the
+// token is handed back only when the LAST connection of that pod closes
+static int g_conns[GEMHOOK_MAX_SLOTS];
+static pthread_mutex_t g_conns_mu = PTHREAD_MUTEX_INITIALIZER;
 static std::string g_dir = ".", g_file = "resource-config.txt", g_mirror;
 static int g_swap = 0, g_verbose = 0;
 
@@ -121,7 +125,7 @@ static void* conn_main(void* arg) {
   setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
   uint8_t in[GEMHOOK_REQ_LEN], out[GEMHOOK_RSP_LEN];
   uint64_t held = 0;  // bytes this connection reserved (allocation_map[sockfd], pod-manager.cpp:92)
-  int held_slot = -1, token_slot = -1;
+  int held_slot = -1, token_slot = -1, counted_slot = -1;
   while (recv_all(fd, in, sizeof(in)) == 0) {
     gemhook_request req;
     if (gemhook_wire_unpack_request(in, &req) < 0) break;
@@ -129,6 +133,12 @@ static void* conn_main(void* arg) {
     if (slot < 0) {  // gem-schd: "Unknown client ... Ignore this request" (scheduler.cpp:411-414) -> no reply
       fprintf(stderr, "[gem-arbiter] unknown client \"%s\": request ignored\n", req.name);
       continue;
+    }
+    if (counted_slot < 0 && slot < GEMHOOK_MAX_SLOTS) {
+      pthread_mutex_lock(&g_conns_mu);
+      g_conns[slot]++;
+      pthread_mutex_unlock(&g_conns_mu);
+      counted_slot = slot;
     }
     gemhook_response rsp;
     memset(&rsp, 0, sizeof(rsp));
@@ -158,8 +168,15 @@ static void* conn_main(void* arg) {
     if (send_all(fd, out, sizeof(out)) != 0) break;
   }
   if (held && held_slot >= 0) gemhook_pool_mem_release(g_pool, held_slot, held);  // process gone: reclaim
-  // a client that disappears while holding the token must not stall the others until its deadline
-  if (token_slot >= 0) gemhook_pool_release(g_pool, token_slot);
+  bool last = true;
+  if (counted_slot >= 0) {
+    pthread_mutex_lock(&g_conns_mu);
+    last = --g_conns[counted_slot] == 0;
+    pthread_mutex_unlock(&g_conns_mu);
+  }
+  // a pod that disappears while holding the token must not stall the others until its deadline -- but only when its
+  // last process is gone (a sibling may be running kernels under that token)
+  if (token_slot >= 0 && last) gemhook_pool_release(g_pool, token_slot);
   close(fd);
   return nullptr;
 }

@@ -478,17 +478,22 @@ int main(int argc, char** argv) {
     if (re == CUDA_SUCCESS && g) cuGraphGetNodes(g, NULL, &nodes);
     CUresult ri = (re == CUDA_SUCCESS && g) ? cuGraphInstantiateWithFlags(&ge, g, 0) : CUDA_ERROR_INVALID_VALUE;
     CUresult rr = CUDA_SUCCESS;
+    double replay_ms = 0; /* the application's own measurement of its replays: an event pair around each */
     for (long r = 0; r < rounds && ri == CUDA_SUCCESS && rr == CUDA_SUCCESS; r++) {
+      cuEventRecord(e0, cs);
       rr = cuGraphLaunch(ge, cs);
+      cuEventRecord(e1, cs);
       if (rr == CUDA_SUCCESS) rr = cuStreamSynchronize(cs);
+      float ms = 0;
+      if (rr == CUDA_SUCCESS && cuEventElapsedTime(&ms, e0, e1) == CUDA_SUCCESS) replay_ms += ms;
     }
     CUresult rs = cuCtxSynchronize();
     CUresult rd = cuStreamDestroy(cs);
     for (int i = 0; i < 64; i++) CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
     CK(cuCtxSynchronize());
     fprintf(out, "{\"mode\": \"graph\", \"begin\": %d, \"launch\": %d, \"end\": %d, \"nodes\": %zu, \"instantiate\": %d, "
-            "\"replay\": %d, \"sync\": %d, \"destroy\": %d, \"captured\": %ld, \"replays\": %ld}\n",
-            (int)rb, (int)rl, (int)re, nodes, (int)ri, (int)rr, (int)rs, (int)rd, step_launches, rounds);
+            "\"replay\": %d, \"sync\": %d, \"destroy\": %d, \"captured\": %ld, \"replays\": %ld, \"replay_ms\": %.6f}\n",
+            (int)rb, (int)rl, (int)re, nodes, (int)ri, (int)rr, (int)rs, (int)rd, step_launches, rounds, replay_ms);
   } else if (!strcmp(mode, "probe")) {
     /* host cost (ns) of the building blocks; medians would be nicer, means over 20k are stable enough */
     const int N = 20000;

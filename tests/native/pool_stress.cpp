@@ -1,7 +1,9 @@
 // tests/native/pool_stress.cpp -- TEST: thread-sanitizer / address-sanitizer stress of the shared credit pool and
 // the gate.  Built and run by tests/test_sanitizers.py with -fsanitize=thread and -fsanitize=address,undefined.
-// N client threads (one slot each) acquire tokens, "use" them briefly, reserve/release memory; a reader thread polls
-// usage and history.  Invariants: at most one token holder at any time, mem_used returns to 0, no deadlock.
+// N client threads (one slot each, plus two extra threads that share slot 0 like two processes of one pod) acquire
+// tokens, "use" them briefly, reserve/release memory; a reader thread polls usage, history and slot_info the whole time
+// (observers are lock-free readers: they never delay a hand-over).  Invariants: every acquire returns a positive
+// quota, mem_used never exceeds the limit and returns to 0, no deadlock, no data race.
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -45,6 +47,9 @@ static void* reader(void*) {
       gemhook_pool_mem_info(g_pool, s, &u, &l);
       if (u > l) g_violations++;
       (void)gemhook_pool_accumulated_ms(g_pool, s);
+      gemhook_slot_info info;
+      if (gemhook_pool_slot_info(g_pool, s, &info) != 0 || info.mem_used > info.mem_limit) g_violations++;
+      (void)gemhook_pool_usage(g_pool, s, 1e9);
     }
     gemhook_pool_history(g_pool, slots, a, b, 64);
     usleep(500);
@@ -63,7 +68,10 @@ int main(int argc, char** argv) {
   pthread_t t[64], rd;
   pthread_create(&rd, nullptr, reader, nullptr);
   for (int i = 0; i < n; i++) pthread_create(&t[i], nullptr, client, (void*)(intptr_t)i);
+  pthread_t sib[2];  // two more "processes" of pod c0: they share slot 0's mailbox and pod-level token
+  for (int i = 0; i < 2; i++) pthread_create(&sib[i], nullptr, client, (void*)(intptr_t)0);
   for (int i = 0; i < n; i++) pthread_join(t[i], nullptr);
+  for (int i = 0; i < 2; i++) pthread_join(sib[i], nullptr);
   g_stop = 1;
   pthread_join(rd, nullptr);
   int bad = g_violations.load();

@@ -132,30 +132,38 @@ def _three_arms(fracs, wargs):
 def test_config2_two_client_ledger_split_matches_reference():
     """configs[1], the headline config: 2 x 0.5, 30 x 65536 noop launches each, sync every 1024."""
     res = _three_arms([0.5, 0.5], ["--mode", "storm", "--steps", 30, "--warmup", 2, "--step-launches", 65536, "--sync-every", 1024])
-    ref = res["reference"]
+    # The two clients are identical (same fraction, same work); which of them wins the very first token is a coin
+    # toss that decides who ends up with the longer token sequence, so the comparison is between the SORTED per-client
+    # sums (smaller with smaller, larger with larger), not between labels.
+    ref = sorted(res["reference"]["closed_ms"].values())
     for arm in ("ours-tcp", "pool"):
-        got = res[arm]
-        for c in (0, 1):
+        got = sorted(res[arm]["closed_ms"].values())
+        for g, r in zip(got, ref):
             # delivered token time per client: within 1 % of what the reference stack's own ledger says
-            assert abs(got["closed_ms"][c] - ref["closed_ms"][c]) <= 0.01 * ref["closed_ms"][c], (arm, c, res)
-        share = got["closed_ms"][0] / (got["closed_ms"][0] + got["closed_ms"][1])
-        rshare = ref["closed_ms"][0] / (ref["closed_ms"][0] + ref["closed_ms"][1])
-        assert abs(share - rshare) <= 0.01, (arm, share, rshare)
+            assert abs(g - r) <= 0.01 * r, (arm, got, ref)
+        assert abs(got[0] / sum(got) - ref[0] / sum(ref)) <= 0.01, (arm, got, ref)   # and so is the split
+        assert sorted(res[arm]["tokens"].values()) == sorted(res["reference"]["tokens"].values()), (arm, res)
 
 
 @need_ref
 def test_config5_four_client_mixed_fraction_ledger_matches_reference():
     """configs[4] on one device: min-fractions 0.1/0.1/0.4/0.4, MNIST-shaped conv, 60 iterations x 100 launches."""
-    res = _three_arms([0.1, 0.1, 0.4, 0.4], ["--mode", "mnist", "--iters", 60])
+    res = _three_arms([0.1, 0.1, 0.4, 0.4], ["--mode", "mnist", "--iters", 400])
+    # 40 000 launches per client (~6 s of GPU work each): the adaptive quota settles near the 15 ms bursts, so every client
+    # is granted hundreds of tokens and dropping its last one costs well under 1 %.  Clients of one fraction class are
+    # interchangeable (first-token coin toss), so classes are compared sorted.
     ref = res["reference"]
     tot_ref = sum(ref["closed_ms"].values())
     for arm in ("ours-tcp", "pool"):
         got = res[arm]
         tot = sum(got["closed_ms"].values())
         assert abs(tot - tot_ref) <= 0.01 * tot_ref, (arm, tot, tot_ref)   # the same work holds the GPU equally long
-        for c in range(4):
-            # same work per client -> same delivered token time per client (each client's last token excluded)
-            assert abs(got["closed_ms"][c] - ref["closed_ms"][c]) <= 0.02 * ref["closed_ms"][c] + 20.0, (arm, c, res)
+        for cls in ((0, 1), (2, 3)):
+            g = sorted(got["closed_ms"][c] for c in cls)
+            r = sorted(ref["closed_ms"][c] for c in cls)
+            assert abs(sum(g) - sum(r)) <= 0.01 * sum(r), (arm, cls, g, r)
+            for a, b in zip(g, r):
+                assert abs(a - b) <= 0.02 * b, (arm, cls, g, r)   # per client: 2 % (one 20 ms token is 0.3 % here)
 
 
 def test_config3_quota_sequence_equals_oracle_ema_replay():
@@ -261,7 +269,8 @@ def test_cuda_graph_capture_and_replay_under_the_hook():
         st = stats(tmp)[0]
     assert [res[k] for k in ("begin", "launch", "end", "instantiate", "replay", "sync", "destroy")] == [0] * 7, res
     assert res["nodes"] == 64, "our events must not become nodes of the application's graph: %s" % res
-    assert st["gpu_ns"] == st["gpu_ns_host"] > 0.8 * 20 * 64 * 20e3   # the replays were accounted (20 x 64 x 20 us)
+    print("graph replays: app-side events %.3f ms, hook %.3f ms" % (res["replay_ms"], st["gpu_ns"] / 1e6))
+    assert st["gpu_ns"] == st["gpu_ns_host"] >= 0.95 * res["replay_ms"] * 1e6   # the replays were accounted
     script = r'''
 import json, torch
 x = torch.zeros(1 << 16, device="cuda")
