@@ -542,6 +542,12 @@ def main():
         if not args.skip_roofline:
             w0 = time.time()
             roof = roofline_kernel(args.steps, args.warmup, nslots=args.nslots)
+            try:  # the same kernel with the slot table full (GEMHOOK_MAX_SLOTS = 64 clients): bins crowd shared memory
+                r64 = roofline_kernel(args.steps, args.warmup, nslots=64, sizes=(("ring_2p26", 1 << 26),), cpu=False)
+                roof["slots_64"] = r64["ring_2p26"]
+                roof["kernel_launches"] += r64["kernel_launches"]
+            except Exception as e:  # noqa: BLE001
+                log("64-slot roofline leg failed: %r" % (e,))
             windows.append((w0, time.time()))
         if os.path.exists(os.path.join(REFDIR, "libgemhook_ref.so.1")) and not args.skip_baseline:
             for key, m, k_steps in (("cpu_baseline", "reference", args.steps), ("cpu_baseline_debug", "reference-dbg", min(args.steps, 6))):
@@ -641,12 +647,15 @@ def main():
             except (OSError, ValueError, KeyError):
                 pass
             small = {k: {kk: (round(vv, 5) if isinstance(vv, float) else vv) for kk, vv in roof[k].items() if kk in ("records", "avg_ms", "gbps", "grid")}
-                     for k in roof if k.startswith("ring_") and k != "ring_2p26"}
+                     for k in roof if k.startswith("ring_") and k != "ring_2p26" and isinstance(roof[k], dict)}
             line["roofline"] = {"bound": "hbm", "kernel": "gemhook_acct_reduce", "achieved": big["gbps"], "peak": peak,
                                 "unit": "GB/s", "frac": big["gbps"] / peak,
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                                 "traffic": traffic, "algorithmic_bytes": big["bytes"], "records": big["records"], "avg_ms": big["avg_ms"],
                                 "grid": big["grid"], "nslots": args.nslots, "small_rings": small, "cpu_oracle": roof.get("cpu_oracle")}
+            if roof.get("slots_64"):
+                line["roofline"]["slots_64"] = {"achieved": round(roof["slots_64"]["gbps"], 1), "frac": round(roof["slots_64"]["gbps"] / peak, 4),
+                                                "avg_ms": round(roof["slots_64"]["avg_ms"], 5), "grid": roof["slots_64"]["grid"]}
         for key in ("cpu_baseline", "cpu_baseline_debug"):
             r = base_runs.get(key)
             if not r:

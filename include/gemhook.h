@@ -210,6 +210,9 @@ double gemhook_pool_pod_granted(gemhook_pool *, int slot, int64_t now_us, double
 int gemhook_pool_mem_reserve(gemhook_pool *, int slot, uint64_t bytes);   /* 1 ok, 0 over the cap */
 void gemhook_pool_mem_release(gemhook_pool *, int slot, uint64_t bytes);
 void gemhook_pool_mem_info(const gemhook_pool *, int slot, uint64_t *used, uint64_t *limit);
+/* host address of the slot's shared counter words {mem_used, mem_limit (mirror), gpu_ns, launches}: the words the hook
+ * page-locks and device-maps (cuMemHostRegister), i.e. what device code reads when it looks at the pool. */
+const void *gemhook_pool_shared_words(const gemhook_pool *, int slot);
 
 /* byte rules for arrays / pitch (hook.cpp:629-680) */
 uint64_t gemhook_array_bytes(uint64_t w, uint64_t h, uint64_t d, uint32_t channels, uint32_t format, int is3d);
@@ -244,8 +247,16 @@ int gemhook_acct_sync(gemhook_acct *);   /* wait for the accounting stream */
 int gemhook_acct_reset(gemhook_acct *);  /* zero running totals (stream-ordered) */
 uint64_t gemhook_acct_kernel_launches(const gemhook_acct *); /* our own kernels launched so far */
 uint64_t gemhook_acct_stream(const gemhook_acct *);           /* CUstream handle of the accounting stream */
-/* grid the kernel uses for n records (blocks), for the bench's roofline arithmetic */
+/* grid the kernel uses for n records (blocks), for the bench's roofline arithmetic (1 = the one-warp fast path) */
 uint32_t gemhook_acct_grid_for(const gemhook_acct *, size_t n);
+/* gpu_mem mirror (north_star b): the authoritative counter is the CAS word in the shared-pinned pool; (used, limit) of the
+ * process's pod are handed to every reduce launch, whose publish step leaves them in device memory and in the totals
+ * page.  read_mem: from_device = 0 reads the page (no CUDA call), 1 copies the device-resident words back. */
+void gemhook_acct_set_mem(gemhook_acct *, uint32_t slot, uint64_t used, uint64_t limit);
+int gemhook_acct_read_mem(gemhook_acct *, int from_device, uint64_t *slot, uint64_t *used, uint64_t *limit, uint64_t *epoch);
+/* "shared-pinned" check: read four u64 words of host memory (e.g. gemhook_pool_shared_words) THROUGH THE DEVICE -- the
+ * page is cuMemHostRegister'ed for the call unless the caller already did -- and return them. */
+int gemhook_acct_peek_host_words(gemhook_acct *, const void *host_words, uint64_t out[4]);
 
 /* ===================================================================================================
  * (2e) live hook introspection (the process that has libgemhook.so.1 preloaded)

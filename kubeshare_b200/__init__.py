@@ -114,6 +114,10 @@ def lib():
         "gemhook_acct_sync": (C.c_int, [vp]), "gemhook_acct_reset": (C.c_int, [vp]),
         "gemhook_acct_kernel_launches": (u64, [vp]), "gemhook_acct_stream": (u64, [vp]),
         "gemhook_acct_grid_for": (u32, [vp, sz]),
+        "gemhook_acct_set_mem": (None, [vp, u32, u64, u64]),
+        "gemhook_acct_read_mem": (C.c_int, [vp, C.c_int, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "gemhook_acct_peek_host_words": (C.c_int, [vp, vp, C.POINTER(u64)]),
+        "gemhook_pool_shared_words": (vp, [vp, C.c_int]),
         "gemhook_get_stats": (C.c_int, [C.POINTER(Stats)]), "gemhook_flush": (C.c_int, []),
         "gemhook_last_error": (cp, []), "gemhook_version": (cp, []),
     }

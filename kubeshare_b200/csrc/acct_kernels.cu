@@ -2,9 +2,9 @@
 //
 // The reference hook has no device code at all: its only GPU-time measurement is one event pair per
 // token resolved on the host (reference Gemini/src/hook.cpp:456-502).  The B200-native hook stamps
-// launch segments with CUDA events (csrc/acct.cpp) and reduces the resulting 16-byte launch records
+// launch segments with CUDA events (csrc/gh_hook.cpp) and reduces the resulting 16-byte launch records
 // on the device, so the per-client running totals live next to the ring in HBM and only one small
-// snapshot per launch crosses to the mapped pinned totals page the host gate reads.
+// snapshot per launch crosses to the mapped pinned totals page the host reads without a CUDA call.
 //
 // Record (16 B, one uint4, see include/gemhook.h gemhook_record):
 //     x = slot            client slot in the credit pool; slot >= nslots is ignored
@@ -14,37 +14,52 @@
 // order-independent, so parity with the CPU oracle is bit-exact.
 //
 // Roofline: pure streaming read, 16 B per record, O(nslots) bytes written per block -> HBM-bound.
-// Design (see DESIGN.md "acct_reduce"):
-//   * every lane loads whole records with 128-bit ld.global.nc.L1::no_allocate (a warp covers
-//     512 contiguous bytes per load, UNROLL independent loads in flight per lane);
-//   * privatised accumulation without atomics: each warp owns a column-major bin table in shared
-//     memory, bins[slot][lane], so lane L only ever touches column L (conflict-free banks, no races);
-//   * block epilogue: columns are folded with __shfl_down_sync, warps are folded through shared
-//     memory, and ONE atomicAdd per (slot, field) per block goes to the device-resident totals;
-//   * the last block to finish (threadfence + ticket) publishes the running totals to the mapped
-//     pinned totals page: double-buffered by epoch parity, one system fence, then the epoch store.
+// Design:
+//   * every lane loads whole records with 128-bit ld.global.nc.L1::no_allocate (a warp covers 512 contiguous
+//     bytes per load); the loads of tile k+1 are issued BEFORE tile k is accumulated (register double buffer), so
+//     every warp keeps UNROLL 16-byte loads per lane in flight all the time -- what decides the bandwidth once the
+//     bin tables of many slots leave room for only a few warps per SM;
+//   * privatised accumulation without atomics: each warp owns bins[slot][lane] in shared memory, one 16-byte cell
+//     per (slot, lane): u64 ns | u64 (count << 48 | launches).  Lane L only ever touches column L: no races, and a
+//     128-bit access per lane is conflict-free per quarter warp.  One LDS.128 + two 64-bit adds + one STS.128 per
+//     record.  The packed half holds < 2^16 records per column, so every FLUSH_EVERY tiles a warp folds its bins
+//     into its own u64 accumulators (never in practice below 2^31 records per launch; tested with a small value);
+//   * epilogue without shuffle trees: lane L sums the 32 columns of slots L, L+32, ... with a rotated column index
+//     (conflict-free), warps are folded through shared memory, ONE atomicAdd per (slot, field) per block;
+//   * the last block to finish (threadfence + ticket) publishes the running totals -- and the mirror of the pod's
+//     gpu_mem counter the host passes along -- to the mapped pinned totals page: double-buffered by epoch parity,
+//     one system fence, then the epoch store;
+//   * gemhook_acct_reduce_small: one warp, no ticket, totals taken from the atomics' return values -- the live
+//     hook's regime (a flush carries tens of records) where fixed costs are everything.
 //
 // Build: nvcc -cubin -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (csrc/Makefile); the cubin
 // is embedded in libgemhook.so.1 and loaded with cuModuleLoadData (no cudart dependency).
 
 #include <stdint.h>
 
-#define GEMHOOK_MAX_WARPS_PER_BLOCK 8  /* host picks 8 or 4 warps by shared-memory budget */
 #ifndef GEMHOOK_UNROLL
-#define GEMHOOK_UNROLL 16              /* independent 16-byte loads in flight per lane (host: gh_acct.cpp TILE_RECORDS) */
+#define GEMHOOK_UNROLL 8               /* 16-byte loads per lane per tile; two tiles are in flight (host: gh_acct.cpp TILE_RECORDS) */
 #endif
-#ifndef GEMHOOK_MIN_BLOCKS
-#define GEMHOOK_MIN_BLOCKS 1
-#endif
+#define GEMHOOK_MAX_WARPS_PER_BLOCK 8
+
+typedef unsigned long long u64;
 
 extern "C" {
 
 #define GEMHOOK_PAGE_MAX_SLOTS 64
 struct gemhook_totals_page {   // mapped pinned page (host reads it without any CUDA call)
-  unsigned long long epoch;    // number of reduce launches published; buf[epoch & 1] holds the current totals
-  unsigned long long nslots;
-  unsigned long long reserved[2];
-  unsigned long long buf[2][GEMHOOK_PAGE_MAX_SLOTS * 3];  // [slot][3]: elapsed_ns, launches, records
+  u64 epoch;                   // number of reduce launches published; buf[epoch & 1] holds the current totals
+  u64 nslots;
+  u64 mem_slot;                // which slot the memory mirror below describes (the publishing process's own pod)
+  u64 reserved;
+  u64 buf[2][GEMHOOK_PAGE_MAX_SLOTS * 3];  // [slot][3]: elapsed_ns, launches, records
+  u64 mem[2][2];               // [epoch parity]: mem_used, mem_limit of mem_slot as the host passed them at launch
+};
+
+// what the host passes along with every launch: the pod's gpu_mem counter (authoritative copy: the CAS word in the
+// shared-pinned credit pool) to be mirrored into device memory and the totals page
+struct gemhook_mem_mirror {
+  u64 slot, used, limit;
 };
 
 __device__ __forceinline__ uint4 ld_stream_16(const uint4* p) {
@@ -55,34 +70,162 @@ __device__ __forceinline__ uint4 ld_stream_16(const uint4* p) {
   return r;
 }
 
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-  return v;
+}  // extern "C"
+
+#define PK_ONE (1ull << 48)
+#define PK_MASK (PK_ONE - 1ull)
+
+// one record into the warp's bins: cell (slot, lane) = {ns, count << 48 | launches}.  Branch-free: a slot outside
+// [0, nslots) lands in the trash row `nslots`, which is zeroed with the others and never folded.
+__device__ __forceinline__ void bin_add(uint4* cells, unsigned nslots, unsigned lane, const uint4& r) {
+  uint4* c = cells + min(r.x, nslots) * 32u + lane;
+  uint4 v = *c;
+  u64 ns = (((u64)v.y << 32) | v.x) + (((u64)r.w << 32) | r.z);
+  u64 pk = (((u64)v.w << 32) | v.z) + (PK_ONE | (u64)r.y);
+  *c = make_uint4((unsigned)ns, (unsigned)(ns >> 32), (unsigned)pk, (unsigned)(pk >> 32));
 }
 
-}  // extern "C" (templates below need C++ linkage)
-
-// Privatised bins, per warp: ns[nslots][COLS] u64 | la[nslots][COLS] u64 | rc[nslots][COLS] u32 (20 B per cell).
-// COLS = 32: every lane owns a column -> plain read-modify-write, no races, conflict-free banks.
-// COLS = 16: lanes L and L+16 share column L and take turns (two phases per tile separated by __syncwarp):
-//            half the shared memory per slot.  The host picks it for nslots > 16: with 32 columns the bins of 20+
-//            slots eat so much of the 228 KB L1/shared array that too few loads can be in flight (measured on B200:
-//            6.5 TB/s up to 16 slots, 5.4 at 20, 4.5 at 32, 2.5 at 64 with 32 columns).
-template <unsigned COLS>
-__device__ __forceinline__ void bin_add(unsigned long long* ns, unsigned long long* la, unsigned* rc,
-                                        unsigned nslots, unsigned col, const uint4& r) {
-  if (r.x < nslots) {
-    unsigned idx = r.x * COLS + col;
-    ns[idx] += ((unsigned long long)r.w << 32) | r.z;
-    la[idx] += r.y;
-    rc[idx] += 1u;
+// fold the warp's bins: lane L owns slots L, L+32, ...; column index rotated by the lane -> conflict-free LDS.128.
+// acc[slot][3] (warp private, u64) += column sums; optionally the bins are zeroed for the next round.
+__device__ __forceinline__ void fold_bins(uint4* cells, u64* acc, unsigned nslots, unsigned lane, bool rezero) {
+  __syncwarp();
+  for (unsigned s = lane; s < nslots; s += 32u) {
+    u64 ns = 0ull, la = 0ull, rc = 0ull;
+#pragma unroll 8
+    for (unsigned c = 0; c < 32u; c++) {
+      uint4 v = cells[s * 32u + ((c + lane) & 31u)];
+      u64 pk = ((u64)v.w << 32) | v.z;
+      ns += ((u64)v.y << 32) | v.x;
+      la += pk & PK_MASK;
+      rc += pk >> 48;
+    }
+    acc[s * 3u + 0u] += ns;
+    acc[s * 3u + 1u] += la;
+    acc[s * 3u + 2u] += rc;
+  }
+  __syncwarp();
+  if (rezero) {
+    for (unsigned s = 0; s <= nslots; s++) cells[s * 32u + lane] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
   }
 }
 
-// Last block of a launch (threadfence + ticket) publishes the running totals to the mapped pinned page.
-__device__ __forceinline__ void publish_totals(unsigned nslots, unsigned long long* __restrict__ dev_totals,
-                                               unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page) {
+// totals -> buf[(e+1) & 1] of the mapped pinned page, ONE system-scope fence, then the 8-byte epoch store that flips
+// the reader over (reader rule: gh_acct.cpp read_page).  The publish counter lives in device memory
+// (dev_totals[nslots*3]) so nothing is ever READ over PCIe here.  Called by all threads of ONE block.
+__device__ __forceinline__ void publish_page(unsigned nslots, u64* __restrict__ dev_totals, gemhook_totals_page* __restrict__ page,
+                                             const gemhook_mem_mirror& mm, u64* __restrict__ dev_mem) {
+  __shared__ u64 e_sh;
+  if (threadIdx.x == 0) e_sh = *reinterpret_cast<volatile u64*>(dev_totals + nslots * 3u) + 1ull;
+  __syncthreads();
+  const u64 e = e_sh;
+  u64* dst = page->buf[e & 1ull];
+  for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
+    // read through L2 (the atomics were resolved there); volatile avoids a stale L1 line
+    dst[t] = *reinterpret_cast<volatile u64*>(dev_totals + t);
+  }
+  if (threadIdx.x == 0) {
+    page->mem[e & 1ull][0] = mm.used;
+    page->mem[e & 1ull][1] = mm.limit;
+    if (dev_mem) {  // device-resident mirror of the pod's gpu_mem counter
+      dev_mem[0] = mm.used;
+      dev_mem[1] = mm.limit;
+      dev_mem[2] = mm.slot;
+      dev_mem[3] = e;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dev_totals[nslots * 3u] = e;
+    page->nslots = nslots;
+    page->mem_slot = mm.slot;
+    *reinterpret_cast<volatile u64*>(&page->epoch) = e;
+  }
+}
+
+extern "C" {
+
+// dev_totals: [nslots][3] u64 running totals + 1 u64 publish counter (device memory, persistent)
+// ticket:     u32 zero-initialised, self-resetting
+// dynamic shared memory: warps * ((nslots + 1) * 512 + nslots * 24) bytes  (bins incl. the trash row, then the warps'
+// u64 accumulators)
+__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 1)
+gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals,
+                    unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm,
+                    u64* __restrict__ dev_mem, unsigned flush_every) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const unsigned nwarps = blockDim.x >> 5;
+  uint4* cells = reinterpret_cast<uint4*>(smem) + (size_t)warp * (nslots + 1u) * 32u;
+  u64* acc = reinterpret_cast<u64*>(smem + (size_t)nwarps * (nslots + 1u) * 512u) + (size_t)warp * nslots * 3u;
+
+  for (unsigned s = 0; s <= nslots; s++) cells[s * 32u + lane] = make_uint4(0u, 0u, 0u, 0u);
+  for (unsigned t = lane; t < nslots * 3u; t += 32u) acc[t] = 0ull;
+  __syncwarp();
+
+  const u64 warps_total = (u64)gridDim.x * nwarps;
+  const u64 tile = 32ull * GEMHOOK_UNROLL;  // records per warp-iteration
+  u64 base = ((u64)blockIdx.x * nwarps + warp) * tile;
+  const u64 stride = warps_total * tile;
+  unsigned since_flush = 0;
+
+  uint4 a[GEMHOOK_UNROLL], b[GEMHOOK_UNROLL];
+  bool va = base + tile <= n;
+  if (va) {
+#pragma unroll
+    for (int u = 0; u < GEMHOOK_UNROLL; u++) a[u] = ld_stream_16(rec + base + (unsigned)u * 32u + lane);
+  }
+  while (va) {
+    // tile A is in registers (or on its way): put tile B in flight, then accumulate A
+    u64 nb = base + stride;
+    const bool vb = nb + tile <= n;
+    if (vb) {
+#pragma unroll
+      for (int u = 0; u < GEMHOOK_UNROLL; u++) b[u] = ld_stream_16(rec + nb + (unsigned)u * 32u + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add(cells, nslots, lane, a[u]);
+    base = nb;
+    if (++since_flush >= flush_every) {
+      fold_bins(cells, acc, nslots, lane, true);
+      since_flush = 0;
+    }
+    if (!vb) break;
+    u64 na = base + stride;
+    va = na + tile <= n;
+    if (va) {
+#pragma unroll
+      for (int u = 0; u < GEMHOOK_UNROLL; u++) a[u] = ld_stream_16(rec + na + (unsigned)u * 32u + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add(cells, nslots, lane, b[u]);
+    base = na;
+    if (++since_flush >= flush_every) {
+      fold_bins(cells, acc, nslots, lane, true);
+      since_flush = 0;
+    }
+  }
+  if (base < n) {  // ragged tail of this warp's last tile
+#pragma unroll 1
+    for (int u = 0; u < GEMHOOK_UNROLL; u++) {
+      u64 i = base + (unsigned)u * 32u + lane;
+      if (i < n) bin_add(cells, nslots, lane, ld_stream_16(rec + i));
+    }
+  }
+  fold_bins(cells, acc, nslots, lane, false);
+  __syncthreads();
+
+  // fold warps: thread t handles (slot, field) t; ONE atomic per (slot, field) per block
+  const u64* acc0 = reinterpret_cast<const u64*>(smem + (size_t)nwarps * (nslots + 1u) * 512u);
+  for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
+    u64 v = 0ull;
+    for (unsigned w = 0; w < nwarps; w++) v += acc0[(size_t)w * nslots * 3u + t];
+    if (v) atomicAdd(dev_totals + t, v);
+  }
+
+  // last block of the launch (threadfence + ticket) publishes
   __shared__ unsigned is_last;
   __threadfence();
   __syncthreads();
@@ -93,159 +236,94 @@ __device__ __forceinline__ void publish_totals(unsigned nslots, unsigned long lo
   }
   __syncthreads();
   if (is_last && page) {
-    // Double-buffered publication: the totals go to the buffer the host is NOT reading (epoch parity), ONE
-    // system-scope fence orders them before the 8-byte epoch store that flips the reader over.  (A seqlock would
-    // need three fences across PCIe; the reader-side rule is in gh_acct.cpp read_page.)  The publish counter lives
-    // in device memory (dev_totals[nslots*3]) so nothing is ever READ over PCIe here.
-    __shared__ unsigned long long e_sh;
     __threadfence();
-    if (threadIdx.x == 0) e_sh = *reinterpret_cast<volatile unsigned long long*>(dev_totals + nslots * 3u) + 1ull;
-    __syncthreads();
-    const unsigned long long e = e_sh;
-    unsigned long long* dst = page->buf[e & 1ull];
-    for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
-      // read through L2 (the atomics above were resolved there); volatile avoids a stale L1 line
-      dst[t] = *reinterpret_cast<volatile unsigned long long*>(dev_totals + t);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      dev_totals[nslots * 3u] = e;
-      page->nslots = nslots;
-      *reinterpret_cast<volatile unsigned long long*>(&page->epoch) = e;
-    }
+    publish_page(nslots, dev_totals, page, mm, dev_mem);
   }
 }
 
-// dev_totals: [nslots][3] u64 running totals + 1 u64 publish counter (device memory, persistent)
-// ticket:     u32 zero-initialised, self-resetting
-template <unsigned COLS>
-__device__ __forceinline__ void acct_reduce_body(const uint4* __restrict__ rec, unsigned long long n, unsigned nslots,
-                                                 unsigned long long* __restrict__ dev_totals,
-                                                 unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page) {
+// The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight
+// warps, no shuffle trees, no ticket; the running totals come back from the atomics themselves, so nothing is re-read.
+// dynamic shared memory: (nslots + 1) * 512 bytes.
+__global__ void __launch_bounds__(32, 1)
+gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned nslots, u64* __restrict__ dev_totals,
+                          gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm, u64* __restrict__ dev_mem) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned warp = threadIdx.x >> 5;
-  const unsigned nwarps = blockDim.x >> 5;
-  const unsigned col = lane & (COLS - 1u);
-  const unsigned per_warp_bytes = nslots * COLS * 20u;
-  unsigned long long* ns = reinterpret_cast<unsigned long long*>(smem + warp * per_warp_bytes);
-  unsigned long long* la = ns + nslots * COLS;
-  unsigned* rc = reinterpret_cast<unsigned*>(la + nslots * COLS);
-
-  if (lane < COLS) {
-    for (unsigned s = 0; s < nslots; s++) {
-      ns[s * COLS + lane] = 0ull;
-      la[s * COLS + lane] = 0ull;
-      rc[s * COLS + lane] = 0u;
+  const unsigned lane = threadIdx.x;
+  uint4* cells = reinterpret_cast<uint4*>(smem);
+  for (unsigned s = 0; s <= nslots; s++) cells[s * 32u + lane] = make_uint4(0u, 0u, 0u, 0u);
+  __syncwarp();
+  // n <= 2048 (host): at most 64 records per lane < 2^16, the packed count cannot overflow
+  for (unsigned base = 0; base < n; base += 32u * 8u) {
+    uint4 r[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      unsigned i = base + (unsigned)u * 32u + lane;
+      r[u] = i < n ? ld_stream_16(rec + i) : make_uint4(0xffffffffu, 0u, 0u, 0u);
     }
+#pragma unroll
+    for (int u = 0; u < 8; u++) bin_add(cells, nslots, lane, r[u]);
   }
   __syncwarp();
-
-  // the per-column record count is u32: a column sees at most 2 n / (32 * warps) records, far below 2^32
-  const unsigned long long warps_total = (unsigned long long)gridDim.x * nwarps;
-  const unsigned long long gwarp = (unsigned long long)blockIdx.x * nwarps + warp;
-  const unsigned long long tile = 32ull * GEMHOOK_UNROLL;  // records per warp-iteration
-  unsigned long long base = gwarp * tile;
-  const unsigned long long stride = warps_total * tile;
-
-  for (; base + tile <= n; base += stride) {
-    uint4 r[GEMHOOK_UNROLL];
-#pragma unroll
-    for (int u = 0; u < GEMHOOK_UNROLL; u++) r[u] = ld_stream_16(rec + base + (unsigned)u * 32u + lane);
-    if (COLS == 32u) {
-#pragma unroll
-      for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add<COLS>(ns, la, rc, nslots, col, r[u]);
-    } else {
-      // lanes sharing a column take turns: phase p = lanes [p*COLS, (p+1)*COLS)
-#pragma unroll
-      for (unsigned ph = 0; ph < 32u / COLS; ph++) {
-        if (lane / COLS == ph) {
-#pragma unroll
-          for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add<COLS>(ns, la, rc, nslots, col, r[u]);
-        }
-        __syncwarp();
-      }
+  const u64 e = *reinterpret_cast<volatile u64*>(dev_totals + nslots * 3u) + 1ull;
+  u64* dst = page ? page->buf[e & 1ull] : nullptr;
+  for (unsigned s = lane; s < nslots; s += 32u) {
+    u64 ns = 0ull, la = 0ull, rc = 0ull;
+#pragma unroll 8
+    for (unsigned c = 0; c < 32u; c++) {
+      uint4 v = cells[s * 32u + ((c + lane) & 31u)];
+      u64 pk = ((u64)v.w << 32) | v.z;
+      ns += ((u64)v.y << 32) | v.x;
+      la += pk & PK_MASK;
+      rc += pk >> 48;
+    }
+    // the kernel is alone on its stream and owns dev_totals: the values the atomics return ARE the old totals
+    u64 t0 = rc ? atomicAdd(dev_totals + s * 3u + 0u, ns) + ns : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 0u);
+    u64 t1 = rc ? atomicAdd(dev_totals + s * 3u + 1u, la) + la : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 1u);
+    u64 t2 = rc ? atomicAdd(dev_totals + s * 3u + 2u, rc) + rc : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 2u);
+    if (dst) {
+      dst[s * 3u + 0u] = t0;
+      dst[s * 3u + 1u] = t1;
+      dst[s * 3u + 2u] = t2;
     }
   }
-  if (base < n) {  // ragged tail of this warp's last tile
-#pragma unroll 1
-    for (int u = 0; u < GEMHOOK_UNROLL; u++) {
-      unsigned long long i = base + (unsigned)u * 32u + lane;
-      uint4 r = make_uint4(0xffffffffu, 0u, 0u, 0u);  // out-of-range slot: ignored
-      if (i < n) r = ld_stream_16(rec + i);
-      if (COLS == 32u) {
-        bin_add<COLS>(ns, la, rc, nslots, col, r);
-      } else {
-        for (unsigned ph = 0; ph < 32u / COLS; ph++) {
-          if (lane / COLS == ph) bin_add<COLS>(ns, la, rc, nslots, col, r);
-          __syncwarp();
-        }
-      }
+  if (lane == 0) {
+    if (page) {
+      page->mem[e & 1ull][0] = mm.used;
+      page->mem[e & 1ull][1] = mm.limit;
+    }
+    if (dev_mem) {
+      dev_mem[0] = mm.used;
+      dev_mem[1] = mm.limit;
+      dev_mem[2] = mm.slot;
+      dev_mem[3] = e;
     }
   }
+  __threadfence_system();
   __syncwarp();
-
-  // fold the columns of every slot with shuffles; lane 0 leaves the warp result in cells 0..2 of the slot's ns row
-  for (unsigned s = 0; s < nslots; s++) {
-    const bool own = lane < COLS;
-    unsigned long long a = warp_sum_u64(own ? ns[s * COLS + lane] : 0ull);
-    unsigned long long l = warp_sum_u64(own ? la[s * COLS + lane] : 0ull);
-    unsigned long long k = warp_sum_u64(own ? (unsigned long long)rc[s * COLS + lane] : 0ull);
-    __syncwarp();
-    if (lane == 0) {
-      ns[s * COLS] = a;
-      ns[s * COLS + 1] = l;
-      ns[s * COLS + 2] = k;
+  if (lane == 0) {
+    dev_totals[nslots * 3u] = e;
+    if (page) {
+      page->nslots = nslots;
+      page->mem_slot = mm.slot;
+      *reinterpret_cast<volatile u64*>(&page->epoch) = e;
     }
   }
-  __syncthreads();
+}
 
-  // fold warps: thread t handles (slot, field) = (t / 3, t % 3)
-  for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
-    unsigned s = t / 3u, f = t % 3u;
-    unsigned long long acc = 0ull;
-    for (unsigned w = 0; w < nwarps; w++) {
-      const unsigned long long* wns = reinterpret_cast<const unsigned long long*>(smem + w * per_warp_bytes);
-      acc += wns[s * COLS + f];
-    }
-    if (acc) atomicAdd(dev_totals + t, acc);
+// Proof of "shared-pinned": read the pod's gpu_mem counter words straight out of the credit pool (host memory, page
+// locked and device-mapped by cuMemHostRegister) from device code and leave them in device memory.  Not on any hot
+// path: launched on demand by gemhook_acct_peek_pool().
+__global__ void gemhook_peek_pool(const volatile u64* __restrict__ pool_words, u64* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    out[0] = pool_words[0];  // mem_used   (SlotShared, gh_pool.cpp)
+    out[1] = pool_words[1];  // mem_limit mirror
+    out[2] = pool_words[2];  // gpu_ns published so far
+    out[3] = pool_words[3];  // launches published so far
   }
-
-  publish_totals(nslots, dev_totals, ticket, page);
-}
-
-
-extern "C" {
-
-__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, GEMHOOK_MIN_BLOCKS)
-gemhook_acct_reduce(const uint4* __restrict__ rec, unsigned long long n, unsigned nslots,
-                    unsigned long long* __restrict__ dev_totals, unsigned* __restrict__ ticket,
-                    gemhook_totals_page* __restrict__ page) {
-  acct_reduce_body<32u>(rec, n, nslots, dev_totals, ticket, page);
-}
-
-// 16-column variant for nslots > 16 (see bin_add)
-__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, GEMHOOK_MIN_BLOCKS)
-gemhook_acct_reduce_c16(const uint4* __restrict__ rec, unsigned long long n, unsigned nslots,
-                        unsigned long long* __restrict__ dev_totals, unsigned* __restrict__ ticket,
-                        gemhook_totals_page* __restrict__ page) {
-  acct_reduce_body<16u>(rec, n, nslots, dev_totals, ticket, page);
-}
-
-// Device-side timestamp: slot_ns_signed[slot] += (kind ? +t : -t) with t = %globaltimer, so a begin/end pair adds
-// its duration.  NOT used by the hook in round 1 (segments are marked with CUDA events, gh_hook.cpp); kept as the
-// building block of the stamp-kernel marking listed in DESIGN.md 7 (a launch costs 2.05 us of host time on the
-// box, an event record 2.65 us plus a 2.7 us elapsed query).
-__global__ void gemhook_stamp(unsigned long long* __restrict__ slot_ns_signed, unsigned slot, unsigned kind) {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  if (kind) atomicAdd(slot_ns_signed + slot, t);
-  else atomicAdd(slot_ns_signed + slot, 0ull - t);
 }
 
 // Zero the running totals (stream-ordered reset).
-__global__ void gemhook_acct_clear(unsigned long long* __restrict__ dev_totals, unsigned n) {
+__global__ void gemhook_acct_clear(u64* __restrict__ dev_totals, unsigned n) {
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dev_totals[i] = 0ull;
 }
 

@@ -27,15 +27,23 @@ namespace {
 struct totals_page {  // mirrors gemhook_totals_page in acct_kernels.cu
   volatile uint64_t epoch;
   volatile uint64_t nslots;
-  uint64_t reserved[2];
+  volatile uint64_t mem_slot;
+  uint64_t reserved;
   volatile uint64_t buf[2][GEMHOOK_MAX_SLOTS * 3];
+  volatile uint64_t mem[2][2];
+};
+struct mem_mirror {  // mirrors gemhook_mem_mirror (kernel parameter, by value)
+  uint64_t slot, used, limit;
 };
 
-const unsigned BIN_CELL_BYTES = 20u;  // u64 ns + u64 launches + u32 count per (slot, column)
 #ifndef GEMHOOK_UNROLL
-#define GEMHOOK_UNROLL 16
+#define GEMHOOK_UNROLL 8
 #endif
 const unsigned TILE_RECORDS = 32u * GEMHOOK_UNROLL;  // records per warp iteration (32 lanes x GEMHOOK_UNROLL)
+const size_t SMALL_N = 2048;                         // up to here one warp does everything (gemhook_acct_reduce_small)
+// shared memory per warp: (nslots + 1) rows of 32 16-byte cells (the extra row swallows out-of-range slots) + the
+// warp's u64 accumulators
+inline unsigned warp_smem(unsigned nslots) { return (nslots + 1u) * 512u + nslots * 24u; }
 
 const char* cu_err(CUresult r) {
   const char* s = nullptr;
@@ -57,15 +65,17 @@ const char* cu_err(CUresult r) {
 struct gemhook_acct {
   CUcontext ctx = nullptr;
   CUmodule mod = nullptr;
-  CUfunction f_reduce = nullptr, f_clear = nullptr, f_stamp = nullptr;
+  CUfunction f_reduce = nullptr, f_small = nullptr, f_clear = nullptr, f_peek = nullptr;
   CUstream stream = nullptr;
   CUevent ev0 = nullptr, ev1 = nullptr;
-  CUdeviceptr d_ring = 0, d_totals = 0, d_ticket = 0, d_page = 0;
+  CUdeviceptr d_ring = 0, d_totals = 0, d_ticket = 0, d_page = 0, d_mem = 0;
   totals_page* page = nullptr;
   size_t ring_cap = 0;
   uint32_t nslots = 0;
-  unsigned warps = 8, cols = 32, smem_bytes = 0, max_blocks = 0;
+  unsigned warps = 8, smem_bytes = 0, small_smem = 0, max_blocks = 0, flush_every = 8000;
   int sm_count = 0;
+  mem_mirror mm = {0, 0, 0};
+  bool small_enabled = true;
   std::atomic<uint64_t> kernel_launches{0};
   pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
 };
@@ -92,51 +102,48 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
     return -1;
   }
   CU_TRY(GH_CALL(cuModuleLoadData, &a->mod, (const void*)_binary_acct_kernels_cubin_start));
-  // Launch shape by slot count, from the sweep in profiles/r01_acct_reduce_nslots_sweep.jsonl (N = 2^26, B200):
-  //   <= 16 slots: 32 bin columns (every lane owns one), 8 warps/block           6.5-6.7 TB/s
-  //   17-24      : 16 columns (two lanes share one, two phases), 4 warps/block   5.5 TB/s
-  //   25-40      : 32 columns, 2 warps/block, bins may use 208 KB of the SM      4.9 TB/s
-  //   > 40       : 16 columns, 2 warps/block, 208 KB                             3.3 TB/s
-  // (shared memory and L1 share one 228 KB array; large bin tables leave few L1 sectors for loads in flight, and
-  //  the two-phase update of the 16-column layout costs ~15 % by itself -- both measured)
-  unsigned cap_kb = 160;
-  a->cols = 32;
-  a->warps = 8;
-  if (nslots > 40) { a->cols = 16; a->warps = 2; cap_kb = 208; }
-  else if (nslots > 24) { a->cols = 32; a->warps = 2; cap_kb = 208; }
-  else if (nslots > 16) { a->cols = 16; a->warps = 4; cap_kb = 128; }
-  if (const char* e = getenv("GEMHOOK_ACCT_COLS")) {
-    unsigned c = (unsigned)atoi(e);
-    if (c == 16u || c == 32u) a->cols = c;
-  }
+  // Launch shape.  Bins cost warp_smem(nslots) per warp (8.9 KB at 16 slots, 34.8 KB at 64); the kernel keeps two tiles of
+  // UNROLL 16-byte loads per lane in flight per warp (register double buffer, 128 registers at UNROLL 8), so the
+  // register file allows 16 warps per SM and a handful of warps already covers the HBM latency x bandwidth product
+  // (~36 KB in flight per SM).  Warps per SM = min(16, what fits into ~216 KB of shared memory), split into one or two
+  // blocks; the grid is one full wave (a multiple of the SM count), grid-stride over 256-record warp tiles.
+  const unsigned per_warp = warp_smem(nslots);
+  unsigned total = (216u * 1024u) / per_warp;
+  if (total > 16u) total = 16u;
+  if (total < 1u) total = 1u;
+  unsigned blocks_per_sm = total > 8u ? 2u : 1u;
+  a->warps = total / blocks_per_sm;
   if (const char* e = getenv("GEMHOOK_ACCT_WARPS")) {
     unsigned w = (unsigned)atoi(e);
-    if (w == 1u || w == 2u || w == 4u || w == 8u) a->warps = w;
+    if (w >= 1u && w <= 8u && w * per_warp <= 227u * 1024u) a->warps = w;
   }
-  if (const char* e = getenv("GEMHOOK_ACCT_SMEM_CAP_KB")) cap_kb = (unsigned)atoi(e);
-  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod,
-                 a->cols == 32u ? "gemhook_acct_reduce" : "gemhook_acct_reduce_c16"));
+  if (const char* e = getenv("GEMHOOK_ACCT_BLOCKS_PER_SM")) {
+    unsigned b = (unsigned)atoi(e);
+    if (b >= 1u && b <= 8u) blocks_per_sm = b;
+  }
+  if (const char* e = getenv("GEMHOOK_ACCT_FLUSH_EVERY")) {  // tests: force the in-kernel bin flush (default: every 8000 tiles)
+    unsigned f = (unsigned)atoi(e);
+    if (f >= 1u && f <= 8000u) a->flush_every = f;
+  }
+  if (const char* e = getenv("GEMHOOK_ACCT_SMALL")) a->small_enabled = atoi(e) != 0;
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, "gemhook_acct_reduce"));
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_small, a->mod, "gemhook_acct_reduce_small"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_clear, a->mod, "gemhook_acct_clear"));
-  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_stamp, a->mod, "gemhook_stamp"));
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_peek, a->mod, "gemhook_peek_pool"));
   CU_TRY(GH_CALL(cuStreamCreate, &a->stream, CU_STREAM_NON_BLOCKING));
   CU_TRY(GH_CALL(cuEventCreate, &a->ev0, CU_EVENT_DEFAULT));
   CU_TRY(GH_CALL(cuEventCreate, &a->ev1, CU_EVENT_DEFAULT));
 
   a->nslots = nslots;
-  // privatised bins: warps x nslots x cols x 20 B of shared memory per block; resident blocks per SM are limited so
-  // that their bins stay under cap_kb
-  const unsigned per_warp = nslots * a->cols * BIN_CELL_BYTES;
-  const unsigned cap = cap_kb * 1024u;
-  while (a->warps > 1u && a->warps * per_warp > 220u * 1024u) a->warps /= 2u;
   a->smem_bytes = a->warps * per_warp;
+  a->small_smem = (nslots + 1u) * 512u;
   if (a->smem_bytes > 48u * 1024u)
     CU_TRY(GH_CALL(cuFuncSetAttribute, a->f_reduce, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)a->smem_bytes));
   int per_sm = 0;
   CU_TRY(GH_CALL(cuOccupancyMaxActiveBlocksPerMultiprocessor, &per_sm, a->f_reduce, (int)(a->warps * 32u),
                  (size_t)a->smem_bytes));
   if (per_sm < 1) per_sm = 1;
-  if ((unsigned)per_sm * a->smem_bytes > cap && a->smem_bytes) per_sm = (int)(cap / a->smem_bytes);
-  if (per_sm < 1) per_sm = 1;
+  if ((unsigned)per_sm > blocks_per_sm) per_sm = (int)blocks_per_sm;
   a->max_blocks = (unsigned)(per_sm * a->sm_count);  // one full wave: a multiple of the SM count
 
   a->ring_cap = ring_cap ? ring_cap : (1u << 16);
@@ -144,16 +151,18 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   size_t tot_bytes = ((size_t)nslots * 3 + 1) * sizeof(uint64_t);
   CU_TRY(GH_CALL(cuMemAlloc_v2, &a->d_totals, tot_bytes));
   CU_TRY(GH_CALL(cuMemAlloc_v2, &a->d_ticket, 256));
+  CU_TRY(GH_CALL(cuMemAlloc_v2, &a->d_mem, 256));  // device-resident mirror of the pod's gpu_mem counter + peek scratch
   CU_TRY(GH_CALL(cuMemsetD8Async, a->d_totals, 0, tot_bytes, a->stream));
   CU_TRY(GH_CALL(cuMemsetD8Async, a->d_ticket, 0, 256, a->stream));
+  CU_TRY(GH_CALL(cuMemsetD8Async, a->d_mem, 0, 256, a->stream));
   void* hp = nullptr;
   CU_TRY(GH_CALL(cuMemHostAlloc, &hp, sizeof(totals_page), CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
   memset(hp, 0, sizeof(totals_page));
   a->page = (totals_page*)hp;
   CU_TRY(GH_CALL(cuMemHostGetDevicePointer_v2, &a->d_page, hp, 0));
   CU_TRY(GH_CALL(cuStreamSynchronize, a->stream));
-  GH_INFO("acct: %d SMs, nslots %u, %u bin columns, %u warps/block, %u B smem, wave %u blocks", a->sm_count, nslots,
-          a->cols, a->warps, a->smem_bytes, a->max_blocks);
+  GH_INFO("acct: %d SMs, nslots %u, %u warps/block, %u B smem, wave %u blocks (%d per SM)", a->sm_count, nslots, a->warps,
+          a->smem_bytes, a->max_blocks, per_sm);
   return 0;
 }
 
@@ -172,6 +181,7 @@ GH_EXPORT void gemhook_acct_destroy(gemhook_acct* a) {
   if (a->d_ring) GH_CALL(cuMemFree_v2, a->d_ring);
   if (a->d_totals) GH_CALL(cuMemFree_v2, a->d_totals);
   if (a->d_ticket) GH_CALL(cuMemFree_v2, a->d_ticket);
+  if (a->d_mem) GH_CALL(cuMemFree_v2, a->d_mem);
   if (a->page) GH_CALL(cuMemFreeHost, (void*)a->page);
   if (a->ev0) GH_CALL(cuEventDestroy_v2, a->ev0);
   if (a->ev1) GH_CALL(cuEventDestroy_v2, a->ev1);
@@ -181,6 +191,7 @@ GH_EXPORT void gemhook_acct_destroy(gemhook_acct* a) {
 }
 
 GH_EXPORT uint32_t gemhook_acct_grid_for(const gemhook_acct* a, size_t n) {
+  if (a->small_enabled && n <= SMALL_N) return 1;
   size_t per_block = (size_t)a->warps * TILE_RECORDS;
   size_t want = (n + per_block - 1) / per_block;
   if (want < 1) want = 1;
@@ -190,14 +201,94 @@ GH_EXPORT uint32_t gemhook_acct_grid_for(const gemhook_acct* a, size_t n) {
 
 // launch the reduction over n records at device address d_rec (stream-ordered, no host sync)
 static int launch_reduce(gemhook_acct* a, CUdeviceptr d_rec, size_t n) {
-  unsigned long long nn = n;
   unsigned ns = a->nslots;
-  void* args[] = {&d_rec, &nn, &ns, &a->d_totals, &a->d_ticket, &a->d_page};
-  unsigned grid = gemhook_acct_grid_for(a, n);
-  CU_TRY(GH_CALL(cuLaunchKernel, a->f_reduce, grid, 1, 1, a->warps * 32u, 1, 1, a->smem_bytes, a->stream, args,
-                 nullptr));
+  if (a->small_enabled && n <= SMALL_N) {  // the live hook's regime: one warp, no ticket
+    unsigned nn = (unsigned)n;
+    void* args[] = {&d_rec, &nn, &ns, &a->d_totals, &a->d_page, &a->mm, &a->d_mem};
+    CU_TRY(GH_CALL(cuLaunchKernel, a->f_small, 1, 1, 1, 32, 1, 1, a->small_smem, a->stream, args, nullptr));
+  } else {
+    unsigned long long nn = n;
+    void* args[] = {&d_rec, &nn, &ns, &a->d_totals, &a->d_ticket, &a->d_page, &a->mm, &a->d_mem, &a->flush_every};
+    unsigned grid = gemhook_acct_grid_for(a, n);
+    CU_TRY(GH_CALL(cuLaunchKernel, a->f_reduce, grid, 1, 1, a->warps * 32u, 1, 1, a->smem_bytes, a->stream, args, nullptr));
+  }
   a->kernel_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+// ---- gpu_mem mirror -----------------------------------------------------------------------------------------------
+// The authoritative counter is the CAS word in the shared-pinned credit pool (gh_pool.cpp SlotShared); the process
+// hands its pod's current (used, limit) to every reduce launch, whose publish step leaves them in device memory and
+// in the totals page next to the SM-time of the same epoch.
+GH_EXPORT void gemhook_acct_set_mem(gemhook_acct* a, uint32_t slot, uint64_t used, uint64_t limit) {
+  if (!a) return;
+  pthread_mutex_lock(&a->mu);
+  a->mm.slot = slot;
+  a->mm.used = used;
+  a->mm.limit = limit;
+  pthread_mutex_unlock(&a->mu);
+}
+// from_device = 0: the copy in the totals page (no CUDA call); 1: copied back from the device-resident words
+GH_EXPORT int gemhook_acct_read_mem(gemhook_acct* a, int from_device, uint64_t* slot, uint64_t* used, uint64_t* limit, uint64_t* epoch) {
+  if (!a) return -1;
+  uint64_t w[4] = {0, 0, 0, 0};
+  if (from_device) {
+    pthread_mutex_lock(&a->mu);
+    CUresult r = GH_CALL(cuStreamSynchronize, a->stream);
+    if (r == CUDA_SUCCESS) r = GH_CALL(cuMemcpyDtoH_v2, w, a->d_mem, sizeof(w));
+    pthread_mutex_unlock(&a->mu);
+    if (r != CUDA_SUCCESS) {
+      gh_set_error("reading the device mem mirror failed: %d", (int)r);
+      return -1;
+    }
+    if (used) *used = w[0];
+    if (limit) *limit = w[1];
+    if (slot) *slot = w[2];
+    if (epoch) *epoch = w[3];
+    return 0;
+  }
+  for (int tries = 0; tries < 1000000; tries++) {
+    uint64_t e1 = a->page->epoch;
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    uint64_t u = a->page->mem[e1 & 1][0], l = a->page->mem[e1 & 1][1], sl = a->page->mem_slot;
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    if (a->page->epoch == e1) {
+      if (used) *used = u;
+      if (limit) *limit = l;
+      if (slot) *slot = sl;
+      if (epoch) *epoch = e1;
+      return 0;
+    }
+  }
+  return -1;
+}
+// "shared-pinned" check: page-lock + device-map the 4 KiB page(s) holding `host_words` (no-op if the caller already
+// registered them -- the hook registers the pool's counter pages), read four u64 words THROUGH THE DEVICE and return them.
+GH_EXPORT int gemhook_acct_peek_host_words(gemhook_acct* a, const void* host_words, uint64_t out[4]) {
+  if (!a || !host_words) return -1;
+  uintptr_t lo = (uintptr_t)host_words & ~(uintptr_t)4095, hi = ((uintptr_t)host_words + 32 + 4095) & ~(uintptr_t)4095;
+  CUresult reg = GH_CALL(cuMemHostRegister_v2, (void*)lo, hi - lo, CU_MEMHOSTREGISTER_PORTABLE | CU_MEMHOSTREGISTER_DEVICEMAP);
+  bool mine = reg == CUDA_SUCCESS;
+  if (!mine && reg != CUDA_ERROR_HOST_MEMORY_ALREADY_REGISTERED) {
+    gh_set_error("cuMemHostRegister of the pool words failed: %d (%s)", (int)reg, cu_err(reg));
+    return -1;
+  }
+  CUdeviceptr d = 0;
+  int rc = -1;
+  pthread_mutex_lock(&a->mu);
+  if (GH_CALL(cuMemHostGetDevicePointer_v2, &d, (void*)host_words, 0) == CUDA_SUCCESS) {
+    CUdeviceptr d_out = a->d_mem + 64;
+    void* args[] = {&d, &d_out};
+    if (GH_CALL(cuLaunchKernel, a->f_peek, 1, 1, 1, 32, 1, 1, 0, a->stream, args, nullptr) == CUDA_SUCCESS &&
+        GH_CALL(cuStreamSynchronize, a->stream) == CUDA_SUCCESS && GH_CALL(cuMemcpyDtoH_v2, out, d_out, 32) == CUDA_SUCCESS) {
+      a->kernel_launches.fetch_add(1, std::memory_order_relaxed);
+      rc = 0;
+    }
+  }
+  pthread_mutex_unlock(&a->mu);
+  if (rc != 0) gh_set_error("device read of the pool words failed");
+  if (mine) GH_CALL(cuMemHostUnregister, (void*)lo);
+  return rc;
 }
 
 GH_EXPORT int gemhook_acct_reduce_device(gemhook_acct* a, uint64_t d_records, size_t n, float* kernel_ms_out) {
@@ -291,6 +382,7 @@ GH_EXPORT int gemhook_acct_reset(gemhook_acct* a) {
   if (r == CUDA_SUCCESS) a->kernel_launches.fetch_add(1, std::memory_order_relaxed);
   if (r == CUDA_SUCCESS) r = GH_CALL(cuStreamSynchronize, a->stream);
   for (uint32_t i = 0; i < a->nslots * 3; i++) a->page->buf[0][i] = a->page->buf[1][i] = 0;
+  // (the page itself is rewritten by the next launch; until then the host copy must not show stale sums)
   pthread_mutex_unlock(&a->mu);
   if (r != CUDA_SUCCESS) {
     gh_set_error("reset failed: %d", (int)r);

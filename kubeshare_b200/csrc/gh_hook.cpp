@@ -29,6 +29,8 @@ int gh_acct_push_async(gemhook_acct* a, const gemhook_record* pinned_records, si
 void gh_pool_add_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches);
 void* gh_pool_region(gemhook_pool* p, size_t* bytes);
 
+void gh_mem_local(uint64_t* free_b, uint64_t* total_b);  // like gh_mem_info, but never an RPC (gh_mem.cpp)
+
 uint32_t gh_gate_open = 0;  // accessed with relaxed __atomic builtins only (plain MOVs on x86, race-free by the book)
 uint64_t gh_launch_count = 0;
 uint32_t gh_seg_mask = 0xffffffffu;
@@ -263,6 +265,11 @@ static void flush_stage_locked(gh_live* L, bool force) {
   if (!L->acct || L->stage_n == 0) return;
   if (!force && L->stage_n < gh_cfg.flush_records) return;
   int b = L->stage_cur;
+  {  // the pod's gpu_mem counter rides along: the launch mirrors it into device memory and the totals page
+    uint64_t fr = 0, tot = 0;
+    gh_mem_local(&fr, &tot);
+    gemhook_acct_set_mem(L->acct, (uint32_t)L->slot, tot - fr, tot);
+  }
   if (gh_acct_push_async(L->acct, L->stage[b], L->stage_n) == 0 && L->stage_done[b]) {
     CUstream as = (CUstream)(uintptr_t)gemhook_acct_stream(L->acct);
     L->stage_inflight[b] = GH_CALL(cuEventRecord, L->stage_done[b], as) == CUDA_SUCCESS;

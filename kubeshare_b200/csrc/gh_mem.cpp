@@ -174,3 +174,18 @@ void gh_mem_info(uint64_t* free_b, uint64_t* total_b) {
   if (free_b) *free_b = used < total ? total - used : 0;  // (a reload may have lowered the limit below what is in use)
   if (total_b) *total_b = total;
 }
+
+// what this process knows without asking anybody: the pool counters, or (TCP transport) its own share and the limit
+// gem-pmgr last reported
+void gh_mem_local(uint64_t* free_b, uint64_t* total_b) {
+  uint64_t used = 0, total = 0;
+  if (gh_live_enabled()) {
+    if (gh_cfg.transport == 1 && gh_live_pool()) gemhook_pool_mem_info(gh_live_pool(), gh_live_slot(), &used, &total);
+    else {
+      used = g_local_used.load();
+      total = g_tcp_limit_known ? g_tcp_limit : 0;
+    }
+  }
+  if (free_b) *free_b = used < total ? total - used : 0;
+  if (total_b) *total_b = total;
+}

@@ -1299,6 +1299,10 @@ GH_EXPORT void gemhook_pool_counters(const gemhook_pool* p, uint64_t* commits, u
   if (recycled) *recycled = p->r->h.recycled.load(std::memory_order_relaxed);
 }
 
+GH_EXPORT const void* gemhook_pool_shared_words(const gemhook_pool* p, int slot) {
+  return (p && slot >= 0 && slot < GEMHOOK_MAX_SLOTS) ? (const void*)&p->r->shared[slot] : nullptr;
+}
+
 void gh_pool_add_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches) {
   p->r->shared[slot].gpu_ns.fetch_add(gpu_ns, std::memory_order_relaxed);
   p->r->shared[slot].launches.fetch_add(launches, std::memory_order_relaxed);

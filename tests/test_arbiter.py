@@ -193,3 +193,50 @@ def test_port_file_listeners_follow_kubeshare_config():
             assert wp.Client("127.0.0.1", a.port, "ns/a").mem_limit() == (0, 100)   # the static -P listener stays
         finally:
             a.close()
+
+
+def test_launcher_script_starts_one_arbiter_per_gpu_uuid():
+    """f4 launcher parity: tools/launcher-multigpus-b200.sh replaces launcher-multigpus.sh + launcher.py (reference
+    launcher-multigpus.sh:21-42): for every GPU UUID nvidia-smi reports it pre-creates the `0` files, starts one
+    gem-arbiter that owns that GPU's pool, mirrors the quota file onto the hostPath and opens the pods' ports."""
+    launcher = os.path.join(kb.HERE, "tools", "launcher-multigpus-b200.sh")
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg, ports, lib, fake = (os.path.join(tmp, d) for d in ("config", "ports", "library", "bin"))
+        for d in (cfg, ports, lib, fake):
+            os.makedirs(d)
+        with open(os.path.join(fake, "nvidia-smi"), "w") as f:     # two GPUs
+            f.write("#!/bin/sh\necho GPU-aaaa\necho GPU-bbbb\n")
+        os.chmod(os.path.join(fake, "nvidia-smi"), 0o755)
+        port = wp.free_port()
+        with open(os.path.join(cfg, "GPU-aaaa"), "w") as f:        # kubeshare-config's column order: limit request
+            f.write("1\nns/pod 1.0 0.5 4096\n")
+        with open(os.path.join(ports, "GPU-aaaa"), "w") as f:
+            f.write("1\nns/pod %d\n" % port)
+        env = dict(os.environ, PATH=fake + ":" + os.environ["PATH"])
+        p = sp.Popen(["bash", launcher, cfg, ports, lib], env=env, stderr=sp.PIPE, start_new_session=True)
+        try:
+            deadline = time.time() + 10
+            while time.time() < deadline and not (os.path.exists(os.path.join(lib, "gemhook-GPU-bbbb.pool")) and
+                                                  os.path.exists(os.path.join(lib, "config-GPU-aaaa"))):
+                time.sleep(0.05)
+            assert open(os.path.join(cfg, "GPU-bbbb")).read().strip() == "0"      # pre-created like launcher-multigpus.sh:26-31
+            assert open(os.path.join(lib, "config-GPU-aaaa")).read() == "1\nns/pod 1.0 0.5 4096\n"   # hostPath mirror
+            for _ in range(100):                                                   # the pod's port is served by GPU a's arbiter
+                try:
+                    c = wp.Client("127.0.0.1", port, "ns/pod")
+                    break
+                except OSError:
+                    time.sleep(0.05)
+            assert c.mem_limit() == (0, 4096)
+            assert c.quota(0.0, 0.0) == 300.0                                      # launcher.py:77-80 defaults
+            c.close()
+            L = kb.lib()
+            h = L.gemhook_pool_open(os.path.join(lib, "gemhook-GPU-aaaa.pool").encode(), 0, 0, 0, 0, 0)
+            import ctypes as C
+            info = kb.SlotInfo()
+            assert L.gemhook_pool_slot_info(h, 0, C.byref(info)) == 0
+            assert (info.min_frac, info.max_frac) == (0.5, 1.0)                    # --columns limit_request applied
+            L.gemhook_pool_close(h)
+        finally:
+            os.killpg(p.pid, 15)
+            p.wait(timeout=10)

@@ -116,3 +116,69 @@ def test_misaligned_pointer_is_rejected(torch_cuda):
             a.reduce_device(t.data_ptr() + 8, 1)
     finally:
         a.close()
+
+
+# ---- round 2: one-warp fast path, in-kernel bin flush, gpu_mem mirror, shared-pinned read ------------------------------
+@pytest.mark.parametrize("nslots", [1, 3, 64])
+@pytest.mark.parametrize("n", [2, 33, 2047, 2048, 2049, 5000])
+def test_fast_path_boundary_and_equivalence(torch_cuda, OL, nslots, n, monkeypatch):
+    """n <= 2048 runs gemhook_acct_reduce_small (one warp, no ticket); the result must not depend on which kernel ran."""
+    r = make_records(n, nslots, seed=n * 17 + nslots, big=True)
+    want = oracle(OL, r, nslots)
+    for small in ("1", "0"):
+        monkeypatch.setenv("GEMHOOK_ACCT_SMALL", small)
+        a = kb.Acct(nslots, ring_capacity=1 << 14)
+        try:
+            assert a.grid_for(n) == (1 if (small == "1" and n <= 2048) else a.grid_for(n))
+            assert (a.reduce_host(r) == want).all()
+            assert (a.reduce_host(r) == want + want).all()     # running totals through the atomics' return values
+        finally:
+            a.close()
+
+
+@pytest.mark.parametrize("every", [1, 3])
+def test_in_kernel_bin_flush_is_exact(torch_cuda, OL, every, monkeypatch):
+    """The packed (count << 48 | launches) half of a bin cell holds < 2^16 records per column; the kernel folds its bins
+    into u64 accumulators every FLUSH_EVERY tiles (8000 in production: never reached below 2^31 records per launch).
+    Forced to 1 / 3 tiles here, with launches = 2^32 - 1 so the packed sum is as large as it gets."""
+    monkeypatch.setenv("GEMHOOK_ACCT_FLUSH_EVERY", str(every))
+    nslots, n = 5, 300_007
+    r = make_records(n, nslots, seed=every, big=True)
+    r["launches"] = 2**32 - 1
+    a = kb.Acct(nslots)
+    try:
+        assert (a.reduce_host(r) == oracle(OL, r, nslots)).all()
+    finally:
+        a.close()
+
+
+def test_gpu_mem_mirror_and_shared_pinned_read(torch_cuda):
+    """north_star (b): the pod's gpu_mem counter is a CAS word in the shared-pinned pool; every reduce launch mirrors
+    (used, limit) into device memory and the totals page, and device code can read the pool words themselves."""
+    import ctypes as C
+
+    L = kb.lib()
+    p = L.gemhook_pool_open(None, 1, 300.0, 20.0, 10000.0, 1)
+    L.gemhook_pool_load_config(p, b"2\nns/a 0.5 1.0 1000000\nns/b 0.5 1.0 77\n", 0)
+    assert L.gemhook_pool_mem_reserve(p, 0, 123456) == 1
+    a = kb.Acct(2)
+    try:
+        u, lim = C.c_uint64(), C.c_uint64()
+        L.gemhook_pool_mem_info(p, 0, C.byref(u), C.byref(lim))
+        L.gemhook_acct_set_mem(a.h, 0, u.value, lim.value)
+        for n in (10, 5000):                       # fast path and main kernel both publish the mirror
+            a.reduce_host(make_records(n, 2, seed=n))
+            for from_device in (0, 1):
+                sl, us, li, ep = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+                assert L.gemhook_acct_read_mem(a.h, from_device, C.byref(sl), C.byref(us), C.byref(li), C.byref(ep)) == 0
+                assert (sl.value, us.value, li.value) == (0, 123456, 1000000) and ep.value >= 1
+        # the device reads the SAME words the host arbitrates on (zero-copy through the registered mapping)
+        words = (C.c_uint64 * 4)()
+        assert L.gemhook_acct_peek_host_words(a.h, L.gemhook_pool_shared_words(p, 0), words) == 0, kb.last_error()
+        assert (words[0], words[1]) == (123456, 1000000)
+        L.gemhook_pool_mem_release(p, 0, 456)
+        assert L.gemhook_acct_peek_host_words(a.h, L.gemhook_pool_shared_words(p, 0), words) == 0
+        assert words[0] == 123000
+    finally:
+        a.close()
+        L.gemhook_pool_close(p)
