@@ -21,8 +21,9 @@
 //     bin tables of many slots leave room for only a few warps per SM;
 //   * privatised accumulation without atomics: each warp owns bins[slot][lane] in shared memory, one 16-byte cell
 //     per (slot, lane): u64 ns | u64 (count << 48 | launches).  Lane L only ever touches column L: no races, and a
-//     128-bit access per lane is conflict-free per quarter warp.  One LDS.128 + two 64-bit adds + one STS.128 per
-//     record.  The packed half holds < 2^16 records per column, so every FLUSH_EVERY tiles a warp folds its bins
+//     128-bit access per lane is conflict-free per quarter warp.  One 16-byte load + two 64-bit adds + one 16-byte
+//     store per record, GEMHOOK_ILP records per lane at a time with same-slot records merged in registers first so the
+//     read-modify-write chains are independent (bin_add_group).  The packed half holds < 2^16 records per column, so every FLUSH_EVERY tiles a warp folds its bins
 //     into its own u64 accumulators (never in practice below 2^31 records per launch; tested with a small value);
 //   * epilogue without shuffle trees: lane L sums the 32 columns of slots L, L+32, ... with a rotated column index
 //     (conflict-free), warps are folded through shared memory, ONE atomicAdd per (slot, field) per block;
@@ -83,6 +84,57 @@ __device__ __forceinline__ void bin_add(uint4* cells, unsigned nslots, unsigned 
   u64 ns = (((u64)v.y << 32) | v.x) + (((u64)r.w << 32) | r.z);
   u64 pk = (((u64)v.w << 32) | v.z) + (PK_ONE | (u64)r.y);
   *c = make_uint4((unsigned)ns, (unsigned)(ns >> 32), (unsigned)pk, (unsigned)(pk >> 32));
+}
+
+// G records of one lane at once.  A read-modify-write of a shared-memory cell is a dependent chain (load -> add ->
+// store -> the next load may hit the same cell), and with few warps per SM (bins of 64 slots leave room for six) that
+// chain, not HBM, sets the pace: measured 0.74 of the roofline at 64 slots with one record at a time.  Records of the
+// group that name the same slot are first merged in registers (the later one is redirected to the trash row), so the G
+// cells are distinct and their loads, adds and stores are independent: G chains in flight per lane instead of one.
+#ifndef GEMHOOK_ILP
+#define GEMHOOK_ILP 4
+#endif
+template <int G>
+__device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
+  unsigned sl[G];
+  u64 ns[G], pk[G];
+#pragma unroll
+  for (int j = 0; j < G; j++) {
+    sl[j] = min(r[j].x, nslots);
+    ns[j] = ((u64)r[j].w << 32) | r[j].z;
+    pk[j] = PK_ONE | (u64)r[j].y;
+  }
+#pragma unroll
+  for (int j = 1; j < G; j++) {
+#pragma unroll
+    for (int i = 0; i < j; i++) {
+      const bool same = sl[j] == sl[i];
+      ns[i] += same ? ns[j] : 0ull;
+      pk[i] += same ? pk[j] : 0ull;
+      sl[j] = same ? nslots : sl[j];  // (what a redirected record still carries goes to the trash row: harmless)
+    }
+  }
+  uint4 v[G];
+#pragma unroll
+  for (int j = 0; j < G; j++) v[j] = cells[sl[j] * 32u + lane];
+#pragma unroll
+  for (int j = 0; j < G; j++) {
+    u64 a = (((u64)v[j].y << 32) | v[j].x) + ns[j];
+    u64 b = (((u64)v[j].w << 32) | v[j].z) + pk[j];
+    v[j] = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
+  }
+  // two redirected records of one group share the trash cell: whichever store lands last wins, nobody reads it
+#pragma unroll
+  for (int j = 0; j < G; j++) cells[sl[j] * 32u + lane] = v[j];
+}
+template <int U>
+__device__ __forceinline__ void bin_add_tile(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
+  constexpr int G = (GEMHOOK_ILP <= U && U % GEMHOOK_ILP == 0) ? GEMHOOK_ILP : 1;
+#pragma unroll
+  for (int u = 0; u < U; u += G) {
+    if (G == 1) bin_add(cells, nslots, lane, r[u]);
+    else bin_add_group<G>(cells, nslots, lane, r + u);
+  }
 }
 
 // fold the warp's bins: lane L owns slots L, L+32, ...; column index rotated by the lane -> conflict-free LDS.128.
@@ -185,8 +237,7 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* 
 #pragma unroll
       for (int u = 0; u < GEMHOOK_UNROLL; u++) b[u] = ld_stream_16(rec + nb + (unsigned)u * 32u + lane);
     }
-#pragma unroll
-    for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add(cells, nslots, lane, a[u]);
+    bin_add_tile<GEMHOOK_UNROLL>(cells, nslots, lane, a);
     base = nb;
     if (++since_flush >= flush_every) {
       fold_bins(cells, acc, nslots, lane, true);
@@ -199,8 +250,7 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* 
 #pragma unroll
       for (int u = 0; u < GEMHOOK_UNROLL; u++) a[u] = ld_stream_16(rec + na + (unsigned)u * 32u + lane);
     }
-#pragma unroll
-    for (int u = 0; u < GEMHOOK_UNROLL; u++) bin_add(cells, nslots, lane, b[u]);
+    bin_add_tile<GEMHOOK_UNROLL>(cells, nslots, lane, b);
     base = na;
     if (++since_flush >= flush_every) {
       fold_bins(cells, acc, nslots, lane, true);
@@ -252,7 +302,7 @@ gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned ns
   uint4* cells = reinterpret_cast<uint4*>(smem);
   for (unsigned s = 0; s <= nslots; s++) cells[s * 32u + lane] = make_uint4(0u, 0u, 0u, 0u);
   __syncwarp();
-  // n <= 2048 (host): at most 64 records per lane < 2^16, the packed count cannot overflow
+  // n <= 512 (host, gh_acct.cpp SMALL_N): a handful of records per lane, the packed count cannot overflow
   for (unsigned base = 0; base < n; base += 32u * 8u) {
     uint4 r[8];
 #pragma unroll
@@ -260,8 +310,7 @@ gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned ns
       unsigned i = base + (unsigned)u * 32u + lane;
       r[u] = i < n ? ld_stream_16(rec + i) : make_uint4(0xffffffffu, 0u, 0u, 0u);
     }
-#pragma unroll
-    for (int u = 0; u < 8; u++) bin_add(cells, nslots, lane, r[u]);
+    bin_add_tile<8>(cells, nslots, lane, r);
   }
   __syncwarp();
   const u64 e = *reinterpret_cast<volatile u64*>(dev_totals + nslots * 3u) + 1ull;

@@ -132,8 +132,10 @@ static void fatal_or_disable(gh_live* L, const char* what) {
 // implicit dependency that invalidates the application's capture -- cuStreamIsCapturing(legacy) reports exactly
 // that case with an error and does not invalidate anything (driver API docs).  The reference never looks
 // (hook.cpp:482-485, 543 record on the legacy stream unconditionally).
-static bool stream_capturing(CUstream s) {
-  if (!gh_real.cuStreamIsCapturing) return false;
+// On the application's OWN launch path the legacy stream needs no check: a launch on the legacy stream while a blocking
+// stream captures has already invalidated that capture by itself (launch_path = true skips the driver call there).
+static bool stream_capturing(CUstream s, bool launch_path = false) {
+  if (!gh_real.cuStreamIsCapturing || (launch_path && !s)) return false;
   CUstreamCaptureStatus st = CU_STREAM_CAPTURE_STATUS_NONE;
   CUresult r = GH_CALL(cuStreamIsCapturing, s, &st);
   return r != CUDA_SUCCESS || st != CU_STREAM_CAPTURE_STATUS_NONE;
@@ -182,6 +184,7 @@ static double token_from_scheduler(gh_live* L, double overuse_ms, double next_bu
 
 // ---- overuse tracker ----------------------------------------------------------------------------------
 static void host_sync_locked(gh_live* L, int64_t now);
+static void gate_edge_locked(gh_live* L, int64_t now);
 static void resolve_pending_locked(gh_live* L, bool may_block, int skip_last = 0);
 static void sync_pre(bool force);
 
@@ -213,7 +216,10 @@ static void* tracker_main(void* arg) {
     float elapsed_ms = 0.f;
     bool measured = false;
     if (!gh_cfg.dry_run) {
-      sync_pre(true);  // close the running accounting segment on its own stream first
+      // (The accounting segment is NOT closed from this thread: an end marker recorded here can overtake a launch
+      //  that already passed the gate but has not reached the driver yet -- that launch would then belong to no
+      //  segment.  Measured on the box: one 1.3 ms graph replay lost per token.  The launching thread closes the
+      //  segment itself, in program order, when it comes for the new token: gh_launch_slow.)
       // while the application captures a graph the legacy stream is off limits: fall back to the host clock
       if (L->token_ev_valid && !stream_capturing((CUstream)0) &&
           GH_CALL(cuEventRecord, L->ev_drain, (CUstream)0) == CUDA_SUCCESS &&
@@ -223,7 +229,7 @@ static void* tracker_main(void* arg) {
     }
     pthread_mutex_lock(&L->mu);
     int64_t now = gh_now_ns();
-    host_sync_locked(L, now);  // burst ends here; next launch re-evaluates the token
+    gate_edge_locked(L, now);  // burst ends here; next launch re-evaluates the token (the segment stays as it is)
     if (L->yielded) elapsed_ms = 0.f;  // token given back early: nothing was overused
     else if (!measured) elapsed_ms = (float)((double)(now - L->last_token_ns) / 1e6);
     L->yielded = false;
@@ -296,13 +302,11 @@ static void seg_begin_locked(gh_live* L, CUstream stream) {
   if (L->seg_open && L->seg_spans_sync) {  // the running segment continues across the sync we just passed
     if (L->seg_sync_return_ns && now > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(now - L->seg_sync_return_ns);
     L->seg_spans_sync = false;
-    if (!stream_capturing(stream)) L->seg_stream = stream;  // (its end marker must go to a stream we may record on)
+    if (!stream_capturing(stream, true)) L->seg_stream = stream;  // (its end marker must go to a stream we may record on)
     return;
   }
-  if (stream_capturing(stream)) {  // launches into a capturing stream do not run now: nothing to time
-    L->seg_open = false;
-    return;
-  }
+  if (L->seg_open && !L->seg_end_recorded) return;  // still running (the gate was closed for another reason): continue it
+  if (stream_capturing(stream, true)) return;      // launches into a capturing stream do not run now: nothing to time
   L->seg_head = (L->seg_head + 1) % SEG_EVENTS;
   if (GH_CALL(cuEventRecord, L->seg_ev[L->seg_head], stream) != CUDA_SUCCESS) return;
   L->seg_open = true;
@@ -314,12 +318,29 @@ static void seg_begin_locked(gh_live* L, CUstream stream) {
   L->seg_first_launch = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
 }
 
+// The launching thread is about to wait for a new token: whatever it has launched so far ends the running segment
+// (the wait itself must not be accounted).  Recorded by the launching thread, so no launch can slip past the marker.
+static void seg_close_for_renewal_locked(gh_live* L) {
+  if (gh_cfg.dry_run || !L->cuda_ready || !L->seg_open || L->seg_end_recorded) return;
+  int64_t now = gh_now_ns();
+  if (L->seg_spans_sync && L->seg_sync_return_ns && now > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(now - L->seg_sync_return_ns);
+  L->seg_spans_sync = false;
+  uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+  int nxt = (L->seg_head + 1) % SEG_EVENTS;
+  if (n != L->seg_first_launch && L->npending < SEG_EVENTS - 2 && !stream_capturing(L->seg_stream) &&
+      GH_CALL(cuEventRecord, L->seg_ev[nxt], L->seg_stream) == CUDA_SUCCESS) {
+    L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch), L->seg_idle_ns};
+    L->seg_head = nxt;
+  }
+  L->seg_open = false;
+}
+
 // every K launches inside a burst (GEMHOOK_SEG_LAUNCHES=K): close the running segment at this point
 void gh_segment_tick(CUstream stream) {
   gh_live* L = g_live;
   if (!L || !L->cuda_ready || gh_cfg.dry_run) return;
   pthread_mutex_lock(&L->mu);
-  if (L->seg_open && L->npending < SEG_EVENTS / 2 - 1 && !stream_capturing(stream)) {
+  if (L->seg_open && L->npending < SEG_EVENTS / 2 - 1 && !stream_capturing(stream, true)) {
     int nxt = (L->seg_head + 1) % SEG_EVENTS;
     if (GH_CALL(cuEventRecord, L->seg_ev[nxt], stream) == CUDA_SUCCESS) {
       uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
@@ -430,9 +451,13 @@ static void resolve_pending_locked(gh_live* L, bool may_block, int skip_last) {
   L->npending = kept;
 }
 
-static void host_sync_locked(gh_live* L, int64_t now) {
+static void gate_edge_locked(gh_live* L, int64_t now) {
   gemhook_gate_host_sync(L->gate, now);
   __atomic_store_n(&gh_gate_open, 0u, __ATOMIC_RELAXED);
+}
+
+static void host_sync_locked(gh_live* L, int64_t now) {
+  gate_edge_locked(L, now);
   if (L->seg_open && L->seg_spans_sync && !L->seg_end_recorded) L->seg_sync_return_ns = now;  // merged: stays open
   else L->seg_open = false;
 }
@@ -601,6 +626,7 @@ void gh_launch_slow(CUstream stream) {
   }
   if (L->enabled && gemhook_gate_launch_begin(L->gate, now)) {
     L->renewing = true;
+    seg_close_for_renewal_locked(L);
     pthread_mutex_unlock(&L->mu);
     wait_tracker(L);  // GPU drained, overuse known
     pthread_mutex_lock(&L->mu);

@@ -148,6 +148,7 @@ int main(int argc, char** argv) {
 
   if (!strcmp(mode, "storm")) {
     /* un-timed warm-up steps, barrier, then exactly K timed steps */
+    double t_first = now_s(); /* the hook asks for its first token inside the first launch */
     for (long s = 0; s < warmup; s++) {
       for (long i = 1; i <= step_launches; i++) {
         CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
@@ -177,8 +178,8 @@ int main(int argc, char** argv) {
     fprintf(out,
             "{\"mode\": \"storm\", \"client\": %d, \"launches\": %ld, \"steps\": %ld, \"warmup\": %ld, "
             "\"step_launches\": %ld, \"sync_every\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f, \"t0\": %.9f, "
-            "\"t1\": %.9f, \"step_s\": [",
-            client_id, steps * step_launches, steps, warmup, step_launches, sync_every, t1 - t0, ev_ms, t0, t1);
+            "\"t1\": %.9f, \"t_first\": %.9f, \"t_last\": %.9f, \"step_s\": [",
+            client_id, steps * step_launches, steps, warmup, step_launches, sync_every, t1 - t0, ev_ms, t0, t1, t_first, t1);
     for (long s = 0; s < steps; s++) fprintf(out, "%s%.9f", s ? ", " : "", step_s[s]);
     fprintf(out, "]}\n");
   } else if (!strcmp(mode, "bursty")) {
@@ -262,6 +263,12 @@ int main(int argc, char** argv) {
     int c1i = 1, c1o = 32, c2i = 32, c2o = 64;
     void* a1[] = {&d_in, &d_w1, &d_a1, &c1i, &c1o};
     void* a2[] = {&d_a1, &d_w2, &d_a2, &c2i, &c2o};
+    /* the blocking copy is reached the way a cudart application reaches it -- through cuGetProcAddress -- because the
+     * reference hook exports cuMemcpyDtoH C++-mangled by accident (hook.cpp:925-926) and would not see a direct call */
+    typedef CUresult (*dtoh_t)(void*, CUdeviceptr, size_t);
+    dtoh_t dtoh = NULL;
+    CUdriverProcAddressQueryResult qst;
+    CK(cuGetProcAddress("cuMemcpyDtoH", (void**)&dtoh, 12000, CU_GET_PROC_ADDRESS_DEFAULT, &qst));
     barrier(barrier_dir, client_id, nclients, "ready");
     long launches = 0;
     double t0 = now_s();
@@ -272,15 +279,15 @@ int main(int argc, char** argv) {
         CK(cuLaunchKernel(f_conv, 64, N, 1, 28, 28, 1, 0, NULL, a2, NULL));
         launches += 2;
       }
-      CK(cuMemcpyDtoH(host, d_a2, 64 * 4));
+      CK(dtoh(host, d_a2, 64 * 4));
     }
     CK(cuEventRecord(e1, NULL));
     CK(cuEventSynchronize(e1));
     double t1 = now_s();
     float ev_ms = 0;
     CK(cuEventElapsedTime(&ev_ms, e0, e1));
-    fprintf(out, "{\"mode\": \"mnist\", \"client\": %d, \"iters\": %d, \"launches\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f}\n",
-            client_id, iters, launches, t1 - t0, ev_ms);
+    fprintf(out, "{\"mode\": \"mnist\", \"client\": %d, \"iters\": %d, \"launches\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f, "
+            "\"t_first\": %.9f, \"t_last\": %.9f}\n", client_id, iters, launches, t1 - t0, ev_ms, t0, t1);
   } else if (!strcmp(mode, "resolve")) {
     /* the three ways an application reaches the driver: direct symbol, dlsym(), cuGetProcAddress */
     typedef CUresult (*launch_t)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
@@ -522,14 +529,24 @@ int main(int argc, char** argv) {
     t = now_s();
     for (int i = 0; i < 200; i++) CK(cuCtxSynchronize());
     double sync_ns = (now_s() - t) / 200 * 1e9;
+    CUstream ps;
+    CK(cuStreamCreate(&ps, CU_STREAM_NON_BLOCKING));
+    CUstreamCaptureStatus cst;
+    t = now_s();
+    for (int i = 0; i < N; i++) cuStreamIsCapturing(NULL, &cst);
+    double cap0_ns = (now_s() - t) / N * 1e9;
+    t = now_s();
+    for (int i = 0; i < N; i++) cuStreamIsCapturing(ps, &cst);
+    double cap1_ns = (now_s() - t) / N * 1e9;
     struct timespec ts;
     t = now_s();
     for (int i = 0; i < 1000000; i++) clock_gettime(CLOCK_MONOTONIC, &ts);
     double clk_ns = (now_s() - t) / 1e6 * 1e9;
     fprintf(out,
             "{\"mode\": \"probe\", \"launch_ns\": %.1f, \"event_record_ns\": %.1f, \"event_elapsed_ns\": %.1f, "
-            "\"event_query_ns\": %.1f, \"idle_ctx_sync_ns\": %.1f, \"clock_gettime_ns\": %.1f, \"cpus\": %ld}\n",
-            launch_ns, rec_ns, el_ns, q_ns, sync_ns, clk_ns, sysconf(_SC_NPROCESSORS_ONLN));
+            "\"event_query_ns\": %.1f, \"idle_ctx_sync_ns\": %.1f, \"clock_gettime_ns\": %.1f, \"is_capturing_legacy_ns\": %.1f, "
+            "\"is_capturing_stream_ns\": %.1f, \"cpus\": %ld}\n",
+            launch_ns, rec_ns, el_ns, q_ns, sync_ns, clk_ns, cap0_ns, cap1_ns, sysconf(_SC_NPROCESSORS_ONLN));
   } else {
     fprintf(stderr, "gem-storm: unknown mode %s\n", mode);
     return 2;

@@ -55,8 +55,13 @@ def run(nslots, n, env=None, reps=8, flush=None):
 
 
 big = 1 << 26
-for ns in (1, 2, 8, 16, 24, 32, 48, 64):
+quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
+for ns in ((2, 16, 32, 48, 64) if quick else (1, 2, 8, 16, 24, 32, 48, 64)):
     run(ns, big)
+if quick:
+    run(64, big, {"GEMHOOK_ACCT_WARPS": "5"})
+    run(64, big, {"GEMHOOK_ACCT_WARPS": "4"})
+    sys.exit(0)
 # launch-shape overrides where shared memory is the constraint
 for env in ({"GEMHOOK_ACCT_WARPS": "4"}, {"GEMHOOK_ACCT_WARPS": "3", "GEMHOOK_ACCT_BLOCKS_PER_SM": "2"}, {"GEMHOOK_ACCT_WARPS": "2", "GEMHOOK_ACCT_BLOCKS_PER_SM": "3"}):
     run(64, big, env)
@@ -65,7 +70,7 @@ for env in ({"GEMHOOK_ACCT_WARPS": "8", "GEMHOOK_ACCT_BLOCKS_PER_SM": "1"}, {"GE
     run(32, big, env)
 # the live hook's regime: tiny flushes, L2 flushed between launches
 fl = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for n in (2, 64, 1024, 2048):
+for n in (2, 64, 512, 1024):
     for ns in (2, 64):
         run(ns, n, {"GEMHOOK_ACCT_SMALL": "1"}, reps=13, flush=fl)
         run(ns, n, {"GEMHOOK_ACCT_SMALL": "0"}, reps=13, flush=fl)
