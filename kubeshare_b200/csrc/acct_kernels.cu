@@ -76,14 +76,37 @@ __device__ __forceinline__ uint4 ld_stream_16(const uint4* p) {
 #define PK_ONE (1ull << 48)
 #define PK_MASK (PK_ONE - 1ull)
 
+// bin columns per slot: 32 = every lane owns a column; 16 = lanes L and L+16 share column L and take turns (two phases
+// per tile, separated by __syncwarp): half the shared memory per slot, i.e. twice the warps per SM when the slot table
+// is large.  The host (gh_acct.cpp) must be compiled with the same value.
+#ifndef GEMHOOK_COLS
+#define GEMHOOK_COLS 32
+#endif
+#define COLS ((unsigned)GEMHOOK_COLS)
+
+// 16-byte shared-memory accesses spelled out: left to itself the compiler splits the cell load into two LDS.64, which
+// at a 16-byte lane stride is a 2-way bank conflict each; one LDS.128 per cell is conflict-free per quarter warp
+__device__ __forceinline__ uint4 lds128(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint4* p, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
 // one record into the warp's bins: cell (slot, lane) = {ns, count << 48 | launches}.  Branch-free: a slot outside
 // [0, nslots) lands in the trash row `nslots`, which is zeroed with the others and never folded.
-__device__ __forceinline__ void bin_add(uint4* cells, unsigned nslots, unsigned lane, const uint4& r) {
-  uint4* c = cells + min(r.x, nslots) * 32u + lane;
-  uint4 v = *c;
+__device__ __forceinline__ void bin_add(uint4* cells, unsigned nslots, unsigned col, const uint4& r) {
+  uint4* c = cells + min(r.x, nslots) * COLS + col;
+  uint4 v = lds128(c);
   u64 ns = (((u64)v.y << 32) | v.x) + (((u64)r.w << 32) | r.z);
   u64 pk = (((u64)v.w << 32) | v.z) + (PK_ONE | (u64)r.y);
-  *c = make_uint4((unsigned)ns, (unsigned)(ns >> 32), (unsigned)pk, (unsigned)(pk >> 32));
+  sts128(c, make_uint4((unsigned)ns, (unsigned)(ns >> 32), (unsigned)pk, (unsigned)(pk >> 32)));
 }
 
 // G records of one lane at once.  A read-modify-write of a shared-memory cell is a dependent chain (load -> add ->
@@ -95,7 +118,7 @@ __device__ __forceinline__ void bin_add(uint4* cells, unsigned nslots, unsigned 
 #define GEMHOOK_ILP 4
 #endif
 template <int G>
-__device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
+__device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, unsigned col, const uint4* r) {
   unsigned sl[G];
   u64 ns[G], pk[G];
 #pragma unroll
@@ -116,7 +139,7 @@ __device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, uns
   }
   uint4 v[G];
 #pragma unroll
-  for (int j = 0; j < G; j++) v[j] = cells[sl[j] * 32u + lane];
+  for (int j = 0; j < G; j++) v[j] = lds128(cells + sl[j] * COLS + col);
 #pragma unroll
   for (int j = 0; j < G; j++) {
     u64 a = (((u64)v[j].y << 32) | v[j].x) + ns[j];
@@ -125,27 +148,37 @@ __device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, uns
   }
   // two redirected records of one group share the trash cell: whichever store lands last wins, nobody reads it
 #pragma unroll
-  for (int j = 0; j < G; j++) cells[sl[j] * 32u + lane] = v[j];
+  for (int j = 0; j < G; j++) sts128(cells + sl[j] * COLS + col, v[j]);
 }
 template <int U>
 __device__ __forceinline__ void bin_add_tile(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
   constexpr int G = (GEMHOOK_ILP <= U && U % GEMHOOK_ILP == 0) ? GEMHOOK_ILP : 1;
+  const unsigned col = lane & (COLS - 1u);
 #pragma unroll
-  for (int u = 0; u < U; u += G) {
-    if (G == 1) bin_add(cells, nslots, lane, r[u]);
-    else bin_add_group<G>(cells, nslots, lane, r + u);
+  for (unsigned ph = 0; ph < 32u / COLS; ph++) {  // lanes sharing a column take turns
+    if (COLS == 32u || (lane / COLS) == ph) {
+#pragma unroll
+      for (int u = 0; u < U; u += G) {
+        if (G == 1) bin_add(cells, nslots, col, r[u]);
+        else bin_add_group<G>(cells, nslots, col, r + u);
+      }
+    }
+    if (COLS != 32u) __syncwarp();
   }
 }
 
 // fold the warp's bins: lane L owns slots L, L+32, ...; column index rotated by the lane -> conflict-free LDS.128.
 // acc[slot][3] (warp private, u64) += column sums; optionally the bins are zeroed for the next round.
+__device__ __forceinline__ void zero_bins(uint4* cells, unsigned nslots, unsigned lane) {
+  for (unsigned t = lane; t < (nslots + 1u) * COLS; t += 32u) cells[t] = make_uint4(0u, 0u, 0u, 0u);
+}
 __device__ __forceinline__ void fold_bins(uint4* cells, u64* acc, unsigned nslots, unsigned lane, bool rezero) {
   __syncwarp();
   for (unsigned s = lane; s < nslots; s += 32u) {
     u64 ns = 0ull, la = 0ull, rc = 0ull;
 #pragma unroll 8
-    for (unsigned c = 0; c < 32u; c++) {
-      uint4 v = cells[s * 32u + ((c + lane) & 31u)];
+    for (unsigned c = 0; c < COLS; c++) {
+      uint4 v = cells[s * COLS + ((c + lane) & (COLS - 1u))];
       u64 pk = ((u64)v.w << 32) | v.z;
       ns += ((u64)v.y << 32) | v.x;
       la += pk & PK_MASK;
@@ -157,7 +190,7 @@ __device__ __forceinline__ void fold_bins(uint4* cells, u64* acc, unsigned nslot
   }
   __syncwarp();
   if (rezero) {
-    for (unsigned s = 0; s <= nslots; s++) cells[s * 32u + lane] = make_uint4(0u, 0u, 0u, 0u);
+    zero_bins(cells, nslots, lane);
     __syncwarp();
   }
 }
@@ -200,7 +233,7 @@ extern "C" {
 
 // dev_totals: [nslots][3] u64 running totals + 1 u64 publish counter (device memory, persistent)
 // ticket:     u32 zero-initialised, self-resetting
-// dynamic shared memory: warps * ((nslots + 1) * 512 + nslots * 24) bytes  (bins incl. the trash row, then the warps'
+// dynamic shared memory: warps * ((nslots + 1) * COLS * 16 + nslots * 24) bytes  (bins incl. the trash row, then the warps'
 // u64 accumulators)
 __global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 1)
 gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals,
@@ -210,10 +243,10 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const unsigned nwarps = blockDim.x >> 5;
-  uint4* cells = reinterpret_cast<uint4*>(smem) + (size_t)warp * (nslots + 1u) * 32u;
-  u64* acc = reinterpret_cast<u64*>(smem + (size_t)nwarps * (nslots + 1u) * 512u) + (size_t)warp * nslots * 3u;
+  uint4* cells = reinterpret_cast<uint4*>(smem) + (size_t)warp * (nslots + 1u) * COLS;
+  u64* acc = reinterpret_cast<u64*>(smem + (size_t)nwarps * (nslots + 1u) * COLS * 16u) + (size_t)warp * nslots * 3u;
 
-  for (unsigned s = 0; s <= nslots; s++) cells[s * 32u + lane] = make_uint4(0u, 0u, 0u, 0u);
+  zero_bins(cells, nslots, lane);
   for (unsigned t = lane; t < nslots * 3u; t += 32u) acc[t] = 0ull;
   __syncwarp();
 
@@ -261,14 +294,15 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* 
 #pragma unroll 1
     for (int u = 0; u < GEMHOOK_UNROLL; u++) {
       u64 i = base + (unsigned)u * 32u + lane;
-      if (i < n) bin_add(cells, nslots, lane, ld_stream_16(rec + i));
+      const uint4 r = i < n ? ld_stream_16(rec + i) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+      bin_add_tile<1>(cells, nslots, lane, &r);
     }
   }
   fold_bins(cells, acc, nslots, lane, false);
   __syncthreads();
 
   // fold warps: thread t handles (slot, field) t; ONE atomic per (slot, field) per block
-  const u64* acc0 = reinterpret_cast<const u64*>(smem + (size_t)nwarps * (nslots + 1u) * 512u);
+  const u64* acc0 = reinterpret_cast<const u64*>(smem + (size_t)nwarps * (nslots + 1u) * COLS * 16u);
   for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
     u64 v = 0ull;
     for (unsigned w = 0; w < nwarps; w++) v += acc0[(size_t)w * nslots * 3u + t];
@@ -293,14 +327,14 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* 
 
 // The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight
 // warps, no shuffle trees, no ticket; the running totals come back from the atomics themselves, so nothing is re-read.
-// dynamic shared memory: (nslots + 1) * 512 bytes.
+// dynamic shared memory: (nslots + 1) * COLS * 16 bytes.
 __global__ void __launch_bounds__(32, 1)
 gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned nslots, u64* __restrict__ dev_totals,
                           gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm, u64* __restrict__ dev_mem) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned lane = threadIdx.x;
   uint4* cells = reinterpret_cast<uint4*>(smem);
-  for (unsigned s = 0; s <= nslots; s++) cells[s * 32u + lane] = make_uint4(0u, 0u, 0u, 0u);
+  zero_bins(cells, nslots, lane);
   __syncwarp();
   // n <= 512 (host, gh_acct.cpp SMALL_N): a handful of records per lane, the packed count cannot overflow
   for (unsigned base = 0; base < n; base += 32u * 8u) {
@@ -318,8 +352,8 @@ gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned ns
   for (unsigned s = lane; s < nslots; s += 32u) {
     u64 ns = 0ull, la = 0ull, rc = 0ull;
 #pragma unroll 8
-    for (unsigned c = 0; c < 32u; c++) {
-      uint4 v = cells[s * 32u + ((c + lane) & 31u)];
+    for (unsigned c = 0; c < COLS; c++) {
+      uint4 v = cells[s * COLS + ((c + lane) & (COLS - 1u))];
       u64 pk = ((u64)v.w << 32) | v.z;
       ns += ((u64)v.y << 32) | v.x;
       la += pk & PK_MASK;

@@ -44,7 +44,10 @@ const size_t SMALL_N = 512;                          // up to here one warp does
                                                      // measured: 10.5 vs 12.7 us at 2-64 records, break-even near 1024
 // shared memory per warp: (nslots + 1) rows of 32 16-byte cells (the extra row swallows out-of-range slots) + the
 // warp's u64 accumulators
-inline unsigned warp_smem(unsigned nslots) { return (nslots + 1u) * 512u + nslots * 24u; }
+#ifndef GEMHOOK_COLS
+#define GEMHOOK_COLS 32
+#endif
+inline unsigned warp_smem(unsigned nslots) { return (nslots + 1u) * GEMHOOK_COLS * 16u + nslots * 24u; }
 
 const char* cu_err(CUresult r) {
   const char* s = nullptr;
@@ -137,7 +140,7 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
 
   a->nslots = nslots;
   a->smem_bytes = a->warps * per_warp;
-  a->small_smem = (nslots + 1u) * 512u;
+  a->small_smem = (nslots + 1u) * GEMHOOK_COLS * 16u;
   if (a->smem_bytes > 48u * 1024u)
     CU_TRY(GH_CALL(cuFuncSetAttribute, a->f_reduce, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)a->smem_bytes));
   int per_sm = 0;

@@ -294,8 +294,11 @@ static void flush_stage_locked(gh_live* L, bool force) {
   }
 }
 
-static void seg_begin_locked(gh_live* L, CUstream stream) {
-  if (gh_cfg.dry_run || !L->cuda_ready) return;
+// Returns false when the launches that follow are NOT covered by an accounting segment (their stream is being
+// captured, or the marker could not be recorded): the caller then keeps the gate closed, so the next launch comes
+// through here again instead of running unaccounted on the fast path.
+static bool seg_begin_locked(gh_live* L, CUstream stream) {
+  if (gh_cfg.dry_run || !L->cuda_ready) return true;
   // events are a ring: never re-record one that an unresolved segment still refers to
   if (L->npending > SEG_EVENTS / 2) resolve_pending_locked(L, true);
   int64_t now = gh_now_ns();
@@ -303,12 +306,12 @@ static void seg_begin_locked(gh_live* L, CUstream stream) {
     if (L->seg_sync_return_ns && now > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(now - L->seg_sync_return_ns);
     L->seg_spans_sync = false;
     if (!stream_capturing(stream, true)) L->seg_stream = stream;  // (its end marker must go to a stream we may record on)
-    return;
+    return true;
   }
-  if (L->seg_open && !L->seg_end_recorded) return;  // still running (the gate was closed for another reason): continue it
-  if (stream_capturing(stream, true)) return;      // launches into a capturing stream do not run now: nothing to time
+  if (L->seg_open && !L->seg_end_recorded) return true;  // still running (the gate was closed for another reason): continue it
+  if (stream_capturing(stream, true)) return false;      // launches into a capturing stream do not run now: nothing to time
   L->seg_head = (L->seg_head + 1) % SEG_EVENTS;
-  if (GH_CALL(cuEventRecord, L->seg_ev[L->seg_head], stream) != CUDA_SUCCESS) return;
+  if (GH_CALL(cuEventRecord, L->seg_ev[L->seg_head], stream) != CUDA_SUCCESS) return false;
   L->seg_open = true;
   L->seg_end_recorded = false;
   L->seg_spans_sync = false;
@@ -316,6 +319,7 @@ static void seg_begin_locked(gh_live* L, CUstream stream) {
   L->seg_begin_host_ns = now;
   L->seg_idle_ns = 0;
   L->seg_first_launch = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+  return true;
 }
 
 // The launching thread is about to wait for a new token: whatever it has launched so far ends the running segment
@@ -665,8 +669,9 @@ void gh_launch_slow(CUstream stream) {
     pthread_cond_broadcast(&L->renew_cv);
   }
   gemhook_gate_launch_end(L->gate, gh_now_ns());
-  seg_begin_locked(L, stream);
-  __atomic_store_n(&gh_gate_open, 1u, __ATOMIC_RELAXED);
+  // (while a capture is going on the gate stays closed: a capture is short, and the first launch after it must open a
+  //  segment -- measured on the box: with the gate left open the graph replays that followed ran unaccounted)
+  if (seg_begin_locked(L, stream)) __atomic_store_n(&gh_gate_open, 1u, __ATOMIC_RELAXED);
   pthread_mutex_unlock(&L->mu);
 }
 

@@ -427,18 +427,24 @@ struct gemhook_pool {
     if (fcntl(fd, F_OFD_GETLK, &fl) != 0) return true;  // cannot tell: assume alive
     return fl.l_type != F_UNLCK;
   }
+  // The OFD byte is taken BEFORE the entry is marked in use: an entry that reads in_use == 1 is therefore always
+  // vouched for by a held lock (or its owner is dead), and a reaper can never mistake an entry that is still being
+  // set up for a dead one -- it did, once: two live clients then shared one attachment and overwrote each other's burst.
   int take_attachment(int slot) {
     for (uint32_t i = 0; i < MAX_ATTACH; i++) {
+      if (r->attach[i].in_use.load(std::memory_order_acquire) != 0) continue;
+      if (attach_lock((int)i, true) != 0) continue;  // somebody else is setting this entry up (or a stale lock holder lives)
       uint32_t exp = 0;
-      if (r->attach[i].in_use.compare_exchange_strong(exp, 1u)) {
+      if (r->attach[i].in_use.compare_exchange_strong(exp, 3u)) {  // 3 = being initialised: not yet visible to reapers
         Attach& a = r->attach[i];
         a.slot.store(slot);
         a.bytes.store(0);
         a.burst_bits.store(0);
         a.pid = (uint32_t)getpid();
-        attach_lock((int)i, true);
+        a.in_use.store(1u, std::memory_order_release);
         return (int)i;
       }
+      attach_lock((int)i, false);
     }
     return -1;
   }

@@ -250,6 +250,11 @@ int main(int argc, char** argv) {
     fprintf(out, "], \"free_end\": %zu}\n", fr);
   } else if (!strcmp(mode, "mnist")) {
     const int N = 64;
+    /* the very first intercepted call is a launch, so that every hook flavour asks for its first token at the same
+     * point (the reference initialises -- and requests -- inside whichever hooked call comes first, e.g. cuMemAlloc) */
+    double t_first = now_s();
+    CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+    CK(cuCtxSynchronize());
     CUdeviceptr d_in, d_w1, d_a1, d_w2, d_a2;
     CK(cuMemAlloc(&d_in, (size_t)N * 1 * 784 * 4));
     CK(cuMemAlloc(&d_w1, 32 * 1 * 9 * 4));
@@ -287,7 +292,7 @@ int main(int argc, char** argv) {
     float ev_ms = 0;
     CK(cuEventElapsedTime(&ev_ms, e0, e1));
     fprintf(out, "{\"mode\": \"mnist\", \"client\": %d, \"iters\": %d, \"launches\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f, "
-            "\"t_first\": %.9f, \"t_last\": %.9f}\n", client_id, iters, launches, t1 - t0, ev_ms, t0, t1);
+            "\"t_first\": %.9f, \"t_last\": %.9f}\n", client_id, iters, launches, t1 - t0, ev_ms, t_first, t1);
   } else if (!strcmp(mode, "resolve")) {
     /* the three ways an application reaches the driver: direct symbol, dlsym(), cuGetProcAddress */
     typedef CUresult (*launch_t)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
