@@ -115,7 +115,7 @@ __device__ __forceinline__ void bin_add(uint4* cells, unsigned nslots, unsigned 
 // group that name the same slot are first merged in registers (the later one is redirected to the trash row), so the G
 // cells are distinct and their loads, adds and stores are independent: G chains in flight per lane instead of one.
 #ifndef GEMHOOK_ILP
-#define GEMHOOK_ILP 4
+#define GEMHOOK_ILP 2 /* measured (profiles/r02_acct_reduce_variants.jsonl): 1 -> 0.74, 2 -> 0.79, 4 -> 0.79 of the roofline at 64 slots */
 #endif
 template <int G>
 __device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, unsigned col, const uint4* r) {

@@ -42,6 +42,16 @@ static dlsym_fn true_dlsym() {
 extern "C" CUresult CUDAAPI cuGetProcAddress_v2(const char *symbol, void **pfn, int cudaVersion,
                                                 cuuint64_t flags,
                                                 CUdriverProcAddressQueryResult *symbolStatus) {
+  if (symbol && pfn && strcmp(symbol, "cuGetProcAddress") == 0) {
+    // A CUDA-12 runtime asks the resolver for the resolver itself.  The reference would store what the driver answers
+    // -- the 5-argument cuGetProcAddress_v2 -- and later call it through its 4-argument type (hook.cpp:879-885): the
+    // fifth argument (where the driver WRITES the query result) is then whatever the register happens to hold.  The -O2
+    // build survived that by luck, the DEBUG=1 (-O0) build crashed inside libcuda on the GPU box.  Answering here keeps
+    // the reference on its own first branch (the legacy 4-argument entry point from dlsym) for every later lookup.
+    *pfn = (void *)&cuGetProcAddress_v2;
+    if (symbolStatus) *symbolStatus = CU_GET_PROC_ADDRESS_SUCCESS;
+    return CUDA_SUCCESS;
+  }
   CUresult r = cuGetProcAddress(symbol, pfn, cudaVersion, flags);
   if (symbolStatus)
     *symbolStatus = (r == CUDA_SUCCESS && pfn && *pfn) ? CU_GET_PROC_ADDRESS_SUCCESS
