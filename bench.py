@@ -453,6 +453,7 @@ def main():
     ap.add_argument("--headline-clients", type=int, default=2)
     ap.add_argument("--reps", type=int, default=3, help="repetitions of the headline K-step run; value = median")
     ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--skip-other", action="store_true", help="skip the bounded configs[2] / configs[4] samples of the default run")
     ap.add_argument("--skip-baseline", action="store_true", help="skip the reference cpu_baseline legs")
     ap.add_argument("--only-roofline", action="store_true", help="run just the accounting-kernel leg (for ncu)")
     ap.add_argument("--nslots", type=int, default=2, help="slot count of the roofline leg")
@@ -535,6 +536,26 @@ def main():
         log("rank %d clients=%d unhooked %s/s hooked(%s) %s/s (device-timed, per rep)" % (
             rank, c, ["%.0f" % sum(r["launches_per_s_device"] for r in rr) for rr in runs["unhooked"]], mode,
             ["%.0f" % sum(r["launches_per_s_device"] for r in rr) for rr in runs["hooked"]]))
+
+    # bounded samples of BASELINE configs[2] (bursty) and configs[4] (MNIST-shaped, mixed fractions) on this rank's GPU, same
+    # arm: un-hooked vs hooked aggregate launches/s and Jain fairness (full runs: --workload bursty|mnist)
+    other = {}
+    if storm and rank == 0 and not args.skip_other:
+        for wl, k_o in (("bursty", 5), ("mnist", 30)):
+            try:
+                w0 = time.time()
+                un_o = run_clients(wl, 4, k_o, args.warmup, my_gpus[0], "unhooked", core_base(my_gpus[0]))
+                hk_o = run_clients(wl, 4, k_o, args.warmup, my_gpus[0], mode, core_base(my_gpus[0]))
+                windows.append((w0, time.time()))
+                jf, how = fairness(hk_o)
+                other["configs[2] bursty" if wl == "bursty" else "configs[4] mnist"] = {
+                    "sample": workload_spec(wl, 4, k_o, args.warmup)[2].split(": ", 1)[1][:160],
+                    "unhooked_launches_per_s": round(un_o["launches_per_s_device"], 1),
+                    "hooked_launches_per_s": round(hk_o["launches_per_s_device"], 1),
+                    "overhead_pct": round((un_o["launches_per_s_device"] / hk_o["launches_per_s_device"] - 1.0) * 100.0, 3),
+                    "jain_fairness": round(jf, 4), "fairness_of": how}
+            except Exception as e:  # noqa: BLE001 -- a side sample must not take the headline down
+                log("%s sample failed: %r" % (wl, e))
 
     roof = None
     base_runs = {}
@@ -627,6 +648,8 @@ def main():
     }
     if storm:
         line["overhead_pct_single_client_quota_1"] = sweep_out.get("1", {}).get("overhead_pct")
+        if other:
+            line["other_configs"] = other
     else:
         jf, how = fairness(head_runs[0])
         line["unhooked_launches_per_s"] = sweep_out[str(hc)]["unhooked_launches_per_s"]

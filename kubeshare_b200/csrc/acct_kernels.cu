@@ -25,8 +25,10 @@
 //     store per record, GEMHOOK_ILP records per lane at a time with same-slot records merged in registers first so the
 //     read-modify-write chains are independent (bin_add_group).  The packed half holds < 2^16 records per column, so every FLUSH_EVERY tiles a warp folds its bins
 //     into its own u64 accumulators (never in practice below 2^31 records per launch; tested with a small value);
-//   * epilogue without shuffle trees: lane L sums the 32 columns of slots L, L+32, ... with a rotated column index
-//     (conflict-free), warps are folded through shared memory, ONE atomicAdd per (slot, field) per block;
+//   * epilogue: up to four slots (a handful of pods per GPU, the common case) are folded with __shfl_down_sync trees;
+//     beyond that lane L sums the 32 columns of slots L, L+32 itself with a rotated column index (conflict-free, 64
+//     loads instead of 30 shuffles per slot); warps are folded through shared memory, ONE atomicAdd per (slot, field)
+//     per block;
 //   * the last block to finish (threadfence + ticket) publishes the running totals -- and the mirror of the pod's
 //     gpu_mem counter the host passes along -- to the mapped pinned totals page: double-buffered by epoch parity,
 //     one system fence, then the epoch store;
@@ -169,11 +171,42 @@ __device__ __forceinline__ void bin_add_tile(uint4* cells, unsigned nslots, unsi
 
 // fold the warp's bins: lane L owns slots L, L+32, ...; column index rotated by the lane -> conflict-free LDS.128.
 // acc[slot][3] (warp private, u64) += column sums; optionally the bins are zeroed for the next round.
+// Few clients (the common case: a handful of pods per GPU): the classic warp tree.  Every lane contributes the cell of
+// its own column, five __shfl_down_sync steps per field leave the slot's sums in lane 0.  For many slots the
+// transposed fold below is cheaper (2 x 32 loads per lane instead of 30 shuffles per slot).
+#ifndef GEMHOOK_SHFL_SLOTS
+#define GEMHOOK_SHFL_SLOTS 4
+#endif
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ void warp_tree_slot(const uint4* cells, unsigned s, unsigned lane, u64& ns, u64& la, u64& rc) {
+  const bool own = lane < COLS;
+  uint4 v = own ? cells[s * COLS + lane] : make_uint4(0u, 0u, 0u, 0u);
+  u64 pk = ((u64)v.w << 32) | v.z;
+  ns = warp_sum_u64(((u64)v.y << 32) | v.x);
+  la = warp_sum_u64(pk & PK_MASK);
+  rc = warp_sum_u64(pk >> 48);
+}
+
 __device__ __forceinline__ void zero_bins(uint4* cells, unsigned nslots, unsigned lane) {
   for (unsigned t = lane; t < (nslots + 1u) * COLS; t += 32u) cells[t] = make_uint4(0u, 0u, 0u, 0u);
 }
 __device__ __forceinline__ void fold_bins(uint4* cells, u64* acc, unsigned nslots, unsigned lane, bool rezero) {
   __syncwarp();
+  if (nslots <= GEMHOOK_SHFL_SLOTS) {
+    for (unsigned s = 0; s < nslots; s++) {
+      u64 ns, la, rc;
+      warp_tree_slot(cells, s, lane, ns, la, rc);
+      if (lane == 0) {
+        acc[s * 3u + 0u] += ns;
+        acc[s * 3u + 1u] += la;
+        acc[s * 3u + 2u] += rc;
+      }
+    }
+  } else
   for (unsigned s = lane; s < nslots; s += 32u) {
     u64 ns = 0ull, la = 0ull, rc = 0ull;
 #pragma unroll 8
@@ -235,7 +268,7 @@ extern "C" {
 // ticket:     u32 zero-initialised, self-resetting
 // dynamic shared memory: warps * ((nslots + 1) * COLS * 16 + nslots * 24) bytes  (bins incl. the trash row, then the warps'
 // u64 accumulators)
-__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 1)
+__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 2)
 gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals,
                     unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm,
                     u64* __restrict__ dev_mem, unsigned flush_every) {
@@ -349,15 +382,21 @@ gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned ns
   __syncwarp();
   const u64 e = *reinterpret_cast<volatile u64*>(dev_totals + nslots * 3u) + 1ull;
   u64* dst = page ? page->buf[e & 1ull] : nullptr;
-  for (unsigned s = lane; s < nslots; s += 32u) {
+  const bool tree = nslots <= GEMHOOK_SHFL_SLOTS;  // few clients: warp tree, lane 0 owns every slot
+  for (unsigned s = tree ? 0u : lane; s < nslots; s += tree ? 1u : 32u) {
     u64 ns = 0ull, la = 0ull, rc = 0ull;
+    if (tree) {
+      warp_tree_slot(cells, s, lane, ns, la, rc);
+      if (lane != 0) continue;
+    } else {
 #pragma unroll 8
-    for (unsigned c = 0; c < COLS; c++) {
-      uint4 v = cells[s * COLS + ((c + lane) & (COLS - 1u))];
-      u64 pk = ((u64)v.w << 32) | v.z;
-      ns += ((u64)v.y << 32) | v.x;
-      la += pk & PK_MASK;
-      rc += pk >> 48;
+      for (unsigned c = 0; c < COLS; c++) {
+        uint4 v = cells[s * COLS + ((c + lane) & (COLS - 1u))];
+        u64 pk = ((u64)v.w << 32) | v.z;
+        ns += ((u64)v.y << 32) | v.x;
+        la += pk & PK_MASK;
+        rc += pk >> 48;
+      }
     }
     // the kernel is alone on its stream and owns dev_totals: the values the atomics return ARE the old totals
     u64 t0 = rc ? atomicAdd(dev_totals + s * 3u + 0u, ns) + ns : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 0u);

@@ -70,8 +70,9 @@ def test_sigkill_inside_the_pool_protocol_never_stalls_the_survivors():
     """kill -9 at every point of the transaction protocol (after claiming a state block, inside the
     policy code, between control word and publication CAS, between CAS and freeing the old block) and from outside,
     6 worker processes respawned continuously; a monitor process times every pool call it makes.  No call may wait for
-    another process (max CPU per call < 1 ms -- a spinning waiter burns CPU; wall < 100 ms allows for the scheduler on
-    this busy box), everything the dead held is reclaimed, a fresh client gets its token at once."""
+    another process: p99.99 of the wall time per call < 2 ms, maximum < 100 ms (eight busy processes share this
+    container's cores; round 1's lock stalled every client for 1 s after such a kill), everything the dead held is
+    reclaimed, a fresh client gets its token at once."""
     import json
 
     with tempfile.TemporaryDirectory() as tmp:
@@ -85,4 +86,5 @@ def test_sigkill_inside_the_pool_protocol_never_stalls_the_survivors():
         print("pool_kill:", res)
         assert p.returncode == 0 and res["ok"], res
         assert res["kills_inside_protocol"] >= 20 and res["kills_from_outside"] >= 20 and res["blocks_recycled"] >= 10
-        assert res["max_cpu_us"] < 1000 and res["mem_used_after_reap"] == 0 and res["fresh_acquire_ms"] < 500
+        assert res["p9999_wall_us"] < 2000 and res["max_wall_us"] < 100000
+        assert res["mem_used_after_reap"] == 0 and res["fresh_acquire_ms"] < 500
