@@ -119,7 +119,8 @@ struct State {
   uint64_t total_grants;
   uint32_t ledger_len;
   uint32_t ledger_dropped;
-  uint64_t _pad[2];
+  uint64_t quota_stamp;  // (mtime, size) stamp of the quota file this configuration was loaded from; 0 = loaded from text
+  uint64_t _pad;
   PSlot slots[GEMHOOK_MAX_SLOTS];
   Span ledger[LEDGER_CAP];
 };
@@ -758,7 +759,13 @@ GH_EXPORT gemhook_pool* gemhook_pool_open(const char* path, int create, double b
     }
   }
   // a liveness byte for this handle's transactions (clients turn it into their own attachment in attach())
-  if (p->fd >= 0) p->liveness_idx = p->take_attachment(-1);
+  if (p->fd >= 0) {
+    p->liveness_idx = p->take_attachment(-1);
+    if (p->liveness_idx < 0) {  // table full of entries whose owners are gone (crashed tools): clear them out, try again
+      gemhook_pool_reap(p);
+      p->liveness_idx = p->take_attachment(-1);
+    }
+  }
   return p;
 }
 
@@ -792,7 +799,14 @@ void gh_pool_shared_layout(size_t* offset, size_t* stride) {
 // never forgets a client; neither do we until the table is full -- then a slot whose pod has left the file, holds
 // nothing and has nobody attached is given to the newcomer.  A row whose name does not fit is skipped (the reference
 // overflows char[HOST_NAME_MAX] there), the others are still loaded.
+static int load_config_stamped(gemhook_pool* p, const char* text, int swap_columns, uint64_t stamp);
 GH_EXPORT int gemhook_pool_load_config(gemhook_pool* p, const char* text, int swap_columns) {
+  return load_config_stamped(p, text, swap_columns, 0);
+}
+// stamp != 0: apply only if the pool's configuration does not carry this stamp yet -- of N clients that notice the same
+// rewrite of the quota file together, exactly one reloads (a reload resets every client's adaptive quota, so a second,
+// late one would be visible in the quota sequence).  Returns -2 when somebody else had already loaded this version.
+static int load_config_stamped(gemhook_pool* p, const char* text, int swap_columns, uint64_t stamp) {
   if (!p || !text) return -1;
   const char* c = text;
   char* end = nullptr;
@@ -828,10 +842,13 @@ GH_EXPORT int gemhook_pool_load_config(gemhook_pool* p, const char* text, int sw
   uint64_t limits[GEMHOOK_MAX_SLOTS];
   uint32_t nlim = 0;
   bool reused[GEMHOOK_MAX_SLOTS];
+  bool stale = false;
   int loaded = transact(p, [&](Policy& pol) {
     State& s = pol.s;
     int cnt = 0;
     full = false;
+    stale = stamp != 0 && s.quota_stamp == stamp;
+    if (stale) return 0;
     for (uint32_t i = 0; i < GEMHOOK_MAX_SLOTS; i++) reused[i] = false;
     for (uint32_t i = 0; i < s.nslots; i++) s.slots[i].listed = 0;
     // rows of clients we already know keep their slot; new names are placed afterwards
@@ -890,9 +907,12 @@ GH_EXPORT int gemhook_pool_load_config(gemhook_pool* p, const char* text, int sw
     }
     nlim = s.nslots;
     for (uint32_t i = 0; i < s.nslots; i++) limits[i] = s.slots[i].mem_limit;
+    // a half-written file (fewer rows than announced) keeps the old stamp: it will be read again
+    if (parsed == n && !full) s.quota_stamp = stamp;
     pol.dirty = true;
     return cnt;
   });
+  if (stale) return -2;
   for (uint32_t i = 0; i < nlim; i++) {
     if (reused[i]) {
       p->r->shared[i].gpu_ns.store(0, std::memory_order_relaxed);
@@ -919,8 +939,12 @@ GH_EXPORT int gemhook_pool_sync_quota_file(gemhook_pool* p, const char* path, in
   size_t n = fread(text, 1, (1 << 16) - 1, f);
   fclose(f);
   text[n] = 0;
-  int rc = gemhook_pool_load_config(p, text, swap_columns);
+  int rc = load_config_stamped(p, text, swap_columns, stamp);
   free(text);
+  if (rc == -2) {  // another client loaded this very version while we were reading the file
+    p->r->h.quota_stamp.store(stamp, std::memory_order_release);
+    return 0;
+  }
   if (rc < 0) return -1;  // half-written file: keep the old stamp, try again at the next renewal
   p->r->h.quota_stamp.store(stamp, std::memory_order_release);
   return 1;

@@ -143,3 +143,40 @@ time.sleep(60)
             assert h
             L.gemhook_pool_close(h)
         L.gemhook_pool_close(p)
+
+
+def test_racing_clients_reload_a_quota_file_version_exactly_once():
+    """Eight clients notice the same (re)written quota file at the same moment: one of them reloads, the others see that
+    the configuration already carries that file's stamp -- a second reload would reset every client's adaptive quota
+    again and show up in the quota sequence (it did, once, in the EMA-replay test on the GPU box)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        qf = os.path.join(tmp, "quota.txt")
+        with open(qf, "w") as f:
+            f.write("2\nns/a 0.5 1.0 10\nns/b 0.5 1.0 20\n")
+        path = os.path.join(tmp, "pool").encode()
+        handles = [L.gemhook_pool_open(path, 1, 300.0, 20.0, 10000.0, 0) for _ in range(8)]
+        for round_ in range(5):
+            if round_:
+                time.sleep(0.01)
+                with open(qf, "w") as f:
+                    f.write("2\nns/a 0.5 1.0 %d\nns/b 0.5 1.0 20\n" % (10 + round_))
+            before = counters(handles[0])[0]
+            out = [None] * 8
+            go = threading.Barrier(8)
+
+            def work(i):
+                go.wait()
+                out[i] = L.gemhook_pool_sync_quota_file(handles[i], qf.encode(), 0)
+
+            th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            assert sorted(out) == [0] * 7 + [1], out
+            assert counters(handles[0])[0] == before + 1       # one committed transaction
+            u, lim = C.c_uint64(), C.c_uint64()
+            L.gemhook_pool_mem_info(handles[3], 0, C.byref(u), C.byref(lim))
+            assert lim.value == 10 + round_
+        for h in handles:
+            L.gemhook_pool_close(h)
