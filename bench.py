@@ -46,7 +46,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 STORM = os.path.join(ROOT, "kubeshare_b200", "bin", "gem-storm")
-HOOK = os.path.join(ROOT, "kubeshare_b200", "lib", "libgemhook.so.1")
+HOOK = os.environ.get("GEMBENCH_HOOK") or os.path.join(ROOT, "kubeshare_b200", "lib", "libgemhook.so.1")  # (override: A/B runs)
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 STEP_LAUNCHES = int(os.environ.get("GEMBENCH_STEP_LAUNCHES", "65536"))  # override only for the CPU stub tests
 SYNC_EVERY = 1024
@@ -314,6 +314,7 @@ def run_clients(workload, nclients, steps, warmup, gpu, mode, core_base, step_la
         else:
             host_s = max(r["wall_s"] for r in res)
         return {"clients": nclients, "fracs": fracs, "launches": launches, "device_s": dev_s, "host_s": host_s,
+                "step_s": [r.get("step_s") for r in res],
                 "launches_per_s_device": launches / dev_s, "launches_per_s_host": launches / host_s,
                 "per_client_wall_s": [r["wall_s"] for r in res], "per_client_launches": [r["launches"] for r in res],
                 "stats": stats, "ledger_ms": ledger, "window": (wall0, wall1)}

@@ -1,6 +1,6 @@
 // gh_hook.cpp -- the live hook: process singleton, launch slow path, token renewal, overuse tracker,
-// segment accounting.  The per-launch FAST path is in gh_interpose.cpp: one load of gh_gate_open and one
-// relaxed increment -- no mutex, no clock read, no syscall (the reference takes three mutex pairs per
+// segment accounting.  The per-launch FAST path is in gh_interpose.cpp: one load of gh_gate_fast and one plain
+// increment of the thread's own counter -- no mutex, no lock prefix, no clock read, no syscall (the reference takes three mutex pairs per
 // launch: window.record_stop, expiration_status_mutex, burst.record_start; hook.cpp:515-555).
 //
 // Reference behaviour kept (hook.cpp): first-use initialisation incl. a discarded first token (:724-771);
@@ -32,7 +32,33 @@ void* gh_pool_region(gemhook_pool* p, size_t* bytes);
 void gh_mem_local(uint64_t* free_b, uint64_t* total_b);  // like gh_mem_info, but never an RPC (gh_mem.cpp)
 
 uint32_t gh_gate_open = 0;  // accessed with relaxed __atomic builtins only (plain MOVs on x86, race-free by the book)
-uint64_t gh_launch_count = 0;
+uint32_t gh_gate_fast = 0;
+__thread gh_thread_node* gh_tl_node __attribute__((tls_model("initial-exec"))) = nullptr;
+static gh_thread_node* g_thread_nodes = nullptr;  // lock-free push-only list
+
+gh_thread_node* gh_thread_register(void) {
+  gh_thread_node* nd = gh_tl_node;
+  if (nd) return nd;
+  nd = (gh_thread_node*)calloc(1, sizeof(gh_thread_node));
+  if (!nd) return nullptr;
+  gh_thread_node* head = __atomic_load_n(&g_thread_nodes, __ATOMIC_ACQUIRE);
+  do {
+    nd->next = head;
+  } while (!__atomic_compare_exchange_n(&g_thread_nodes, &head, nd, false, __ATOMIC_RELEASE, __ATOMIC_ACQUIRE));
+  gh_tl_node = nd;
+  return nd;
+}
+uint64_t gh_total_launches(void) {
+  uint64_t n = 0;
+  for (gh_thread_node* nd = __atomic_load_n(&g_thread_nodes, __ATOMIC_ACQUIRE); nd; nd = nd->next)
+    n += __atomic_load_n(&nd->count, __ATOMIC_RELAXED);
+  return n;
+}
+void gh_gate_set(uint32_t open) {
+  __atomic_store_n(&gh_gate_open, open, __ATOMIC_RELAXED);
+  // with CU_HOOK_DEBUG every launch goes through the counting slow wrapper, so the fast word stays 0
+  __atomic_store_n(&gh_gate_fast, (open && !__atomic_load_n(&gh_hook_debug, __ATOMIC_RELAXED)) ? 1u : 0u, __ATOMIC_RELAXED);
+}
 uint32_t gh_seg_mask = 0xffffffffu;
 
 namespace {
@@ -318,7 +344,7 @@ static bool seg_begin_locked(gh_live* L, CUstream stream) {
   L->seg_stream = stream;
   L->seg_begin_host_ns = now;
   L->seg_idle_ns = 0;
-  L->seg_first_launch = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+  L->seg_first_launch = gh_total_launches();
   return true;
 }
 
@@ -329,7 +355,7 @@ static void seg_close_for_renewal_locked(gh_live* L) {
   int64_t now = gh_now_ns();
   if (L->seg_spans_sync && L->seg_sync_return_ns && now > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(now - L->seg_sync_return_ns);
   L->seg_spans_sync = false;
-  uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+  uint64_t n = gh_total_launches();
   int nxt = (L->seg_head + 1) % SEG_EVENTS;
   if (n != L->seg_first_launch && L->npending < SEG_EVENTS - 2 && !stream_capturing(L->seg_stream) &&
       GH_CALL(cuEventRecord, L->seg_ev[nxt], L->seg_stream) == CUDA_SUCCESS) {
@@ -347,7 +373,7 @@ void gh_segment_tick(CUstream stream) {
   if (L->seg_open && L->npending < SEG_EVENTS / 2 - 1 && !stream_capturing(stream, true)) {
     int nxt = (L->seg_head + 1) % SEG_EVENTS;
     if (GH_CALL(cuEventRecord, L->seg_ev[nxt], stream) == CUDA_SUCCESS) {
-      uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+      uint64_t n = gh_total_launches();
       L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch), L->seg_idle_ns};
       L->seg_head = nxt;
       L->seg_first_launch = n;
@@ -384,7 +410,7 @@ static void sync_pre(bool force) {
     }
     int nxt = (L->seg_head + 1) % SEG_EVENTS;
     if (GH_CALL(cuEventRecord, L->seg_ev[nxt], L->seg_stream) == CUDA_SUCCESS) {
-      uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+      uint64_t n = gh_total_launches();
       L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch), L->seg_idle_ns};
       L->seg_head = nxt;
       L->seg_end_recorded = true;
@@ -417,13 +443,13 @@ void gh_stream_destroyed(CUstream stream) {
         int64_t t = gh_now_ns();
         if (t > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(t - L->seg_sync_return_ns);
       }
-      uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+      uint64_t n = gh_total_launches();
       L->pending[L->npending++] = {L->seg_head, nxt, (uint32_t)(n - L->seg_first_launch), L->seg_idle_ns};
       L->seg_head = nxt;
     }
     L->seg_open = false;
     L->seg_spans_sync = false;
-    __atomic_store_n(&gh_gate_open, 0u, __ATOMIC_RELAXED);  // the next launch opens a fresh segment on its own stream
+    gh_gate_set(0u);  // the next launch opens a fresh segment on its own stream
   }
   if (L->seg_stream == stream) L->seg_stream = nullptr;
   pthread_mutex_unlock(&L->mu);
@@ -457,7 +483,7 @@ static void resolve_pending_locked(gh_live* L, bool may_block, int skip_last) {
 
 static void gate_edge_locked(gh_live* L, int64_t now) {
   gemhook_gate_host_sync(L->gate, now);
-  __atomic_store_n(&gh_gate_open, 0u, __ATOMIC_RELAXED);
+  gh_gate_set(0u);
 }
 
 static void host_sync_locked(gh_live* L, int64_t now) {
@@ -513,7 +539,7 @@ static void live_init(void) {
   if (gh_cfg.disabled || gh_driver_init() != 0) {
     L->enabled = false;
     g_live = L;
-    __atomic_store_n(&gh_gate_open, 1u, __ATOMIC_RELAXED);  // pass-through
+    gh_gate_set(1u);  // pass-through
     return;
   }
   L->enabled = true;
@@ -550,7 +576,7 @@ static void live_init(void) {
     if (!L->trace) L->trace_cap = 0;
   }
   g_live = L;
-  if (!L->enabled) __atomic_store_n(&gh_gate_open, 1u, __ATOMIC_RELAXED);
+  if (!L->enabled) gh_gate_set(1u);
   // registered after the driver's own atexit handlers (cuInit ran before the first intercepted call),
   // so it runs BEFORE them and CUDA is still usable for the final flush
   gh_register_exit_hook();
@@ -671,7 +697,7 @@ void gh_launch_slow(CUstream stream) {
   gemhook_gate_launch_end(L->gate, gh_now_ns());
   // (while a capture is going on the gate stays closed: a capture is short, and the first launch after it must open a
   //  segment -- measured on the box: with the gate left open the graph replays that followed ran unaccounted)
-  if (seg_begin_locked(L, stream)) __atomic_store_n(&gh_gate_open, 1u, __ATOMIC_RELAXED);
+  if (seg_begin_locked(L, stream)) gh_gate_set(1u);
   pthread_mutex_unlock(&L->mu);
 }
 
@@ -698,7 +724,7 @@ GH_EXPORT int gemhook_get_stats(gemhook_stats* out) {
   memset(out, 0, sizeof(*out));
   gh_live* L = g_live;
   if (!L) return -1;
-  uint64_t n = __atomic_load_n(&gh_launch_count, __ATOMIC_RELAXED);
+  uint64_t n = gh_total_launches();
   out->launches = n;
   out->slow_path = L->slow_path.load();
   out->fast_path = n - (out->slow_path < n ? out->slow_path : n);

@@ -76,10 +76,22 @@ gh_live* gh_live_get(void);  // lazily initialised process singleton (NULL if di
 void gh_launch_slow(CUstream stream);
 void gh_host_sync_pre(void);
 void gh_host_sync_post(void);
-extern uint32_t gh_gate_open;              // 1: burst ongoing and token valid -> fast path (relaxed atomics)
-extern uint64_t gh_launch_count;           // intercepted launches (relaxed)
+extern uint32_t gh_gate_open;              // 1: burst ongoing, token valid, segment open (logical gate; relaxed atomics)
+#define GH_HIDDEN __attribute__((visibility("hidden")))  /* referenced rip-relative from the assembly fast path */
+extern GH_HIDDEN uint32_t gh_gate_fast;    // gh_gate_open && !CU_HOOK_DEBUG: the ONE word the per-launch fast path tests
+// per-thread launch counters: the fast path increments its own thread's node with plain moves (no lock prefix, no
+// shared cache line); readers sum the nodes.  Nodes live for the life of the process.
+struct gh_thread_node {
+  uint64_t count;
+  gh_thread_node* next;
+  char pad[48];
+};
+extern GH_HIDDEN __thread gh_thread_node* gh_tl_node __attribute__((tls_model("initial-exec")));
+gh_thread_node* gh_thread_register(void);  // this thread's node (creates it on first use)
+uint64_t gh_total_launches(void);          // sum over all threads that ever launched
+void gh_gate_set(uint32_t open);           // set the logical gate (and the fast word derived from it)
 extern uint32_t gh_hook_debug;            // CU_HOOK_DEBUG=1: count calls per symbol (relaxed atomics; set once by the config load)
-extern uint32_t gh_seg_mask;               // segment every (mask+1) launches; 0xffffffff = burst edges only
+extern GH_HIDDEN uint32_t gh_seg_mask;               // segment every (mask+1) launches; 0xffffffff = burst edges only
 void gh_segment_tick(CUstream stream);
 void gh_stream_destroyed(CUstream stream);  // cuStreamDestroy pre-hook: a segment open on that stream is closed first
 

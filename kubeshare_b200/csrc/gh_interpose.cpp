@@ -61,14 +61,29 @@ static void* resolve_late(void** slot, const char* name) {
   ((decltype(&name))(gh_real.name ? gh_real.name : resolve_late(&gh_real.name, #name)))
 
 // ---- launches ------------------------------------------------------------------------------------------
-static inline __attribute__((always_inline)) void launch_gate(CUstream hStream) {
-  if (__builtin_expect(__atomic_load_n(&gh_gate_open, __ATOMIC_RELAXED) != 0, 1)) {
-    uint64_t n = __atomic_add_fetch(&gh_launch_count, 1, __ATOMIC_RELAXED);
-    if (__builtin_expect(((uint32_t)n & gh_seg_mask) == 0, 0)) gh_segment_tick(hStream);
-  } else {
-    gh_launch_slow(hStream);
-    __atomic_add_fetch(&gh_launch_count, 1, __ATOMIC_RELAXED);
-  }
+// FAST PATH, shaped by hand because it decides the overhead where the launch storm is host-bound (measured on one of
+// the pool's boxes: 2.01 us per launch un-hooked, so every 20 ns of hook is 1 %).  A launch hook is a leaf that either
+// tail-jumps into the driver with its arguments untouched, or tail-jumps into a same-signature slow twin:
+//     load gh_gate_fast, load this thread's counter node (initial-exec TLS), plain increment, mask test, jmp.
+// No lock prefix (round 1: lock xadd on a shared counter), no register saves (round 1: six pushes and five stack
+// reloads, because the slow-path call sat in the same function).
+static inline __attribute__((always_inline)) bool launch_fast_ok(void) {
+  gh_thread_node* nd = gh_tl_node;
+  if (__builtin_expect(!__atomic_load_n(&gh_gate_fast, __ATOMIC_RELAXED) || !nd, 0)) return false;
+  uint64_t n = nd->count + 1;
+  if (__builtin_expect(((uint32_t)n & gh_seg_mask) == 0, 0)) return false;  // segment tick due: slow twin
+  __atomic_store_n(&nd->count, n, __ATOMIC_RELAXED);
+  return true;
+}
+// everything else: gate closed (burst edge / token), first launch of a thread, CU_HOOK_DEBUG counting, segment tick
+static __attribute__((noinline)) void launch_slow_common(CUstream hStream, int counter) {
+  if (__atomic_load_n(&gh_hook_debug, __ATOMIC_RELAXED)) __atomic_add_fetch(&g_calls[counter], 1, __ATOMIC_RELAXED);
+  gh_thread_node* nd = gh_thread_register();
+  if (__atomic_load_n(&gh_gate_open, __ATOMIC_RELAXED) == 0) gh_launch_slow(hStream);
+  if (!nd) return;
+  uint64_t n = nd->count + 1;
+  __atomic_store_n(&nd->count, n, __ATOMIC_RELAXED);
+  if (((uint32_t)n & gh_seg_mask) == 0 && __atomic_load_n(&gh_gate_open, __ATOMIC_RELAXED)) gh_segment_tick(hStream);
 }
 
 typedef CUresult(CUDAAPI* launch_fn)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
@@ -76,48 +91,93 @@ typedef CUresult(CUDAAPI* launch_fn)(CUfunction, unsigned, unsigned, unsigned, u
 typedef CUresult(CUDAAPI* coop_fn)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                                    CUstream, void**);
 typedef CUresult(CUDAAPI* launchex_fn)(const CUlaunchConfig*, CUfunction, void**, void**);
-
-GH_HOOK cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
-                       unsigned shmem, CUstream hStream, void** params, void** extra) {
-  GH_COUNT(cuLaunchKernel);
-  launch_gate(hStream);
-  return GH_REAL_CORE(cuLaunchKernel)(f, gx, gy, gz, bx, by, bz, shmem, hStream, params, extra);
-}
-GH_HOOK cuLaunchCooperativeKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
-                                  unsigned bz, unsigned shmem, CUstream hStream, void** params) {
-  GH_COUNT(cuLaunchCooperativeKernel);
-  launch_gate(hStream);
-  return GH_REAL_CORE(cuLaunchCooperativeKernel)(f, gx, gy, gz, bx, by, bz, shmem, hStream, params);
-}
+typedef CUresult(CUDAAPI* graphlaunch_fn)(CUgraphExec, CUstream);
 
 static void* p_launch_ptsz;
 static void* p_coop_ptsz;
 static void* p_launchex;
 static void* p_launchex_ptsz;
+static void *p_graphlaunch, *p_graphlaunch_pt;
 #define LATE(slot, name) ((slot) ? (slot) : resolve_late(&(slot), name))
 
-GH_HOOK cuLaunchKernel_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
-                            unsigned shmem, CUstream hStream, void** params, void** extra) {
-  GH_COUNT(cuLaunchKernel);
-  launch_gate(hStream);
-  return ((launch_fn)LATE(p_launch_ptsz, "cuLaunchKernel_ptsz"))(f, gx, gy, gz, bx, by, bz, shmem, hStream, params, extra);
-}
-GH_HOOK cuLaunchCooperativeKernel_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
-                                       unsigned bz, unsigned shmem, CUstream hStream, void** params) {
-  GH_COUNT(cuLaunchCooperativeKernel);
-  launch_gate(hStream);
-  return ((coop_fn)LATE(p_coop_ptsz, "cuLaunchCooperativeKernel_ptsz"))(f, gx, gy, gz, bx, by, bz, shmem, hStream, params);
-}
-GH_HOOK cuLaunchKernelEx(const CUlaunchConfig* config, CUfunction f, void** params, void** extra) {
-  GH_COUNT(cuLaunchKernelEx);
-  launch_gate(config ? config->hStream : nullptr);
-  return ((launchex_fn)LATE(p_launchex, "cuLaunchKernelEx"))(config, f, params, extra);
-}
-GH_HOOK cuLaunchKernelEx_ptsz(const CUlaunchConfig* config, CUfunction f, void** params, void** extra) {
-  GH_COUNT(cuLaunchKernelEx);
-  launch_gate(config ? config->hStream : nullptr);
-  return ((launchex_fn)LATE(p_launchex_ptsz, "cuLaunchKernelEx_ptsz"))(config, f, params, extra);
-}
+// The slow twin has the hook's exact signature, so both exits of the hook are plain jumps.  On x86-64 the hook itself
+// is written in assembly: left to the compiler the "leaf with two tail calls" still saved six registers and copied the
+// five stack arguments to registers and back (it needs scratch registers and does not see that the outgoing stack
+// arguments ARE the incoming ones).  13 instructions, scratch registers rax/r10/r11 only (never argument registers):
+//     real = gh_fastfn_<hook>; gate = gh_gate_fast; node = %fs:gh_tl_node; n = node->count + 1;
+//     if (!real || !gate || !node || !(n & gh_seg_mask)) jmp <hook>_slowtwin;  node->count = n;  jmp *real
+#if defined(__x86_64__) && !defined(GEMHOOK_NO_ASM_FASTPATH)
+#define GH_LAUNCH_ENTRY(name, fn_t, params, args)                                                               \
+  extern "C" {                                                                                                 \
+  __attribute__((visibility("hidden"), used)) void* gh_fastfn_##name = nullptr;                                \
+  }                                                                                                            \
+  asm(".text\n.p2align 5\n.globl " #name "\n.type " #name ",@function\n" #name ":\n"                          \
+      "  endbr64\n"                                                                                            \
+      "  movq gh_fastfn_" #name "(%rip), %rax\n"                                                               \
+      "  testq %rax, %rax\n"                                                                                   \
+      "  jz 1f\n"                                                                                              \
+      "  cmpl $0, gh_gate_fast(%rip)\n"                                                                        \
+      "  je 1f\n"                                                                                              \
+      "  movq gh_tl_node@gottpoff(%rip), %r10\n"                                                               \
+      "  movq %fs:(%r10), %r10\n"                                                                              \
+      "  testq %r10, %r10\n"                                                                                   \
+      "  jz 1f\n"                                                                                              \
+      "  movq (%r10), %r11\n"                                                                                  \
+      "  incq %r11\n"                                                                                          \
+      "  testl %r11d, gh_seg_mask(%rip)\n"                                                                     \
+      "  jz 1f\n"                                                                                              \
+      "  movq %r11, (%r10)\n"                                                                                  \
+      "  jmp *%rax\n"                                                                                          \
+      "1:\n"                                                                                                   \
+      "  jmp " #name "_slowtwin\n"                                                                             \
+      ".size " #name ", .-" #name "\n");
+#define GH_FASTFN_PUBLISH(name, fn) __atomic_store_n(&gh_fastfn_##name, (void*)(fn), __ATOMIC_RELEASE)
+#else
+#define GH_LAUNCH_ENTRY(name, fn_t, params, args)                                                               \
+  static void* gh_fastfn_##name = nullptr;                                                                      \
+  GH_HOOK name params {                                                                                         \
+    fn_t real = (fn_t)__atomic_load_n(&gh_fastfn_##name, __ATOMIC_RELAXED);                                     \
+    if (__builtin_expect(real != nullptr && launch_fast_ok(), 1)) return real args;                             \
+    return name##_slowtwin args;                                                                                \
+  }
+#define GH_FASTFN_PUBLISH(name, fn) __atomic_store_n(&gh_fastfn_##name, (void*)(fn), __ATOMIC_RELEASE)
+#endif
+
+#define GH_LAUNCH_HOOK(name, fn_t, slot, symbol, counter, stream_expr, params, args)                           \
+  extern "C" __attribute__((visibility("hidden"), used, noinline)) CUresult CUDAAPI name##_slowtwin params;     \
+  extern "C" __attribute__((visibility("default"))) CUresult CUDAAPI name params;                               \
+  GH_LAUNCH_ENTRY(name, fn_t, params, args)                                                                     \
+  CUresult CUDAAPI name##_slowtwin params {                                                                     \
+    launch_slow_common(stream_expr, counter);                                                                   \
+    fn_t real = (fn_t)LATE(slot, symbol);                                                                       \
+    GH_FASTFN_PUBLISH(name, real);                                                                              \
+    return real args;                                                                                           \
+  }
+
+#define LAUNCH_PARAMS (CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned shmem, \
+                       CUstream hStream, void** params, void** extra)
+#define LAUNCH_ARGS (f, gx, gy, gz, bx, by, bz, shmem, hStream, params, extra)
+#define COOP_PARAMS (CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned shmem, \
+                     CUstream hStream, void** params)
+#define COOP_ARGS (f, gx, gy, gz, bx, by, bz, shmem, hStream, params)
+#define EX_PARAMS (const CUlaunchConfig* config, CUfunction f, void** params, void** extra)
+#define EX_ARGS (config, f, params, extra)
+
+GH_LAUNCH_HOOK(cuLaunchKernel, launch_fn, gh_real.cuLaunchKernel, "cuLaunchKernel", CNT_cuLaunchKernel, hStream, LAUNCH_PARAMS, LAUNCH_ARGS)
+GH_LAUNCH_HOOK(cuLaunchCooperativeKernel, coop_fn, gh_real.cuLaunchCooperativeKernel, "cuLaunchCooperativeKernel",
+               CNT_cuLaunchCooperativeKernel, hStream, COOP_PARAMS, COOP_ARGS)
+GH_LAUNCH_HOOK(cuLaunchKernel_ptsz, launch_fn, p_launch_ptsz, "cuLaunchKernel_ptsz", CNT_cuLaunchKernel, hStream, LAUNCH_PARAMS, LAUNCH_ARGS)
+GH_LAUNCH_HOOK(cuLaunchCooperativeKernel_ptsz, coop_fn, p_coop_ptsz, "cuLaunchCooperativeKernel_ptsz", CNT_cuLaunchCooperativeKernel,
+               hStream, COOP_PARAMS, COOP_ARGS)
+GH_LAUNCH_HOOK(cuLaunchKernelEx, launchex_fn, p_launchex, "cuLaunchKernelEx", CNT_cuLaunchKernelEx, (config ? config->hStream : nullptr),
+               EX_PARAMS, EX_ARGS)
+GH_LAUNCH_HOOK(cuLaunchKernelEx_ptsz, launchex_fn, p_launchex_ptsz, "cuLaunchKernelEx_ptsz", CNT_cuLaunchKernelEx,
+               (config ? config->hStream : nullptr), EX_PARAMS, EX_ARGS)
+// graph launches pass the token gate like a kernel launch
+GH_LAUNCH_HOOK(cuGraphLaunch, graphlaunch_fn, p_graphlaunch, "cuGraphLaunch", CNT_cuGraphLaunch, hStream, (CUgraphExec g, CUstream hStream),
+               (g, hStream))
+GH_LAUNCH_HOOK(cuGraphLaunch_ptsz, graphlaunch_fn, p_graphlaunch_pt, "cuGraphLaunch_ptsz", CNT_cuGraphLaunch, hStream,
+               (CUgraphExec g, CUstream hStream), (g, hStream))
 
 // ---- gpu_mem cap ----------------------------------------------------------------------------------------
 GH_HOOK cuMemAlloc_v2(CUdeviceptr* dptr, size_t bytesize) {
@@ -287,11 +347,10 @@ GH_SYNC_COPY(CNT_cuMemcpyHtoD, cuMemcpyHtoD_v2_ptds, (htod_fn)LATE(p_htod_ptds, 
 typedef CUresult(CUDAAPI* allocasync_fn)(CUdeviceptr*, size_t, CUstream);
 typedef CUresult(CUDAAPI* allocpool_fn)(CUdeviceptr*, size_t, CUmemoryPool, CUstream);
 typedef CUresult(CUDAAPI* freeasync_fn)(CUdeviceptr, CUstream);
-typedef CUresult(CUDAAPI* graphlaunch_fn)(CUgraphExec, CUstream);
 typedef CUresult(CUDAAPI* streamsync_fn)(CUstream);
 typedef CUresult(CUDAAPI* eventsync_fn)(CUevent);
 static void *p_allocasync, *p_allocasync_pt, *p_allocpool, *p_allocpool_pt, *p_freeasync, *p_freeasync_pt;
-static void *p_graphlaunch, *p_graphlaunch_pt, *p_streamsync, *p_streamsync_pt, *p_eventsync;
+static void *p_streamsync, *p_streamsync_pt, *p_eventsync;
 
 #define GH_ALLOC_ASYNC(name, slot, sym)                                        \
   GH_HOOK name(CUdeviceptr* dptr, size_t bytesize, CUstream hStream) {         \
@@ -332,16 +391,6 @@ GH_HOOK cuMemFreeAsync_ptsz(CUdeviceptr dptr, CUstream hStream) {
   GH_COUNT(cuMemFreeAsync);
   gh_mem_free_key((uint64_t)dptr);
   return ((freeasync_fn)LATE(p_freeasync_pt, "cuMemFreeAsync_ptsz"))(dptr, hStream);
-}
-GH_HOOK cuGraphLaunch(CUgraphExec g, CUstream hStream) {
-  GH_COUNT(cuGraphLaunch);
-  launch_gate(hStream);
-  return ((graphlaunch_fn)LATE(p_graphlaunch, "cuGraphLaunch"))(g, hStream);
-}
-GH_HOOK cuGraphLaunch_ptsz(CUgraphExec g, CUstream hStream) {
-  GH_COUNT(cuGraphLaunch);
-  launch_gate(hStream);
-  return ((graphlaunch_fn)LATE(p_graphlaunch_pt, "cuGraphLaunch_ptsz"))(g, hStream);
 }
 // Virtual-memory-management allocations (PyTorch "expandable segments"): the physical handle is what consumes
 // device memory, so cuMemCreate is charged and cuMemRelease gives it back; mapping / address reservation is free.

@@ -229,6 +229,7 @@ CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, uns
                         unsigned sh, CUstream s, void** p, void** e) {
   __atomic_add_fetch(&n_launch, 1, __ATOMIC_RELAXED);
   if (stub_capturing(s)) return CUDA_SUCCESS; /* captured, not executed */
+  if (kernel_ns() == 0) return CUDA_SUCCESS;  /* STUB_KERNEL_US=0: a free GPU, for measuring the hook's own host cost */
   enqueue(kernel_ns());
   return CUDA_SUCCESS;
 }

@@ -7,7 +7,7 @@
    HOW THE RELEASE-AT-EXIT DEVIATION IS EXCLUDED: a client that exits holding a token keeps it until the quota times
    out in the reference (scheduler.cpp:507-510) but hands it back in ours; that only ever affects
    the LAST token of a client, so in every arm a client's last ledger entry is clipped at the moment the client itself
-   finished (its own CLOCK_MONOTONIC stamp, tied to the scheduler's clock through the first grant) -- what is compared
+   finished (its own CLOCK_MONOTONIC stamp; gem-schd's ledger counts from its process start on the same clock) -- what is compared
    is the token time each client was actually delivered while it ran.  (Dropping the last token instead does not
    work: adaptive quotas grow to ~1 s in a launch storm, so the used part of the last token varies by that much.)
  * configs[2] (4 clients 0.25, bursty): every quota the scheduler policy granted equals the oracle's replay of
@@ -46,16 +46,14 @@ def _kubeshare_dirs():
         pytest.skip("cannot create /kubeshare/library (the reference hook hard-codes it)")
 
 
-def _delivered(spans_by_client, outs):
+def _delivered(spans_by_client, outs, schd_t0):
     """Per client: token time delivered = sum(end - start) over its ledger entries, the LAST one clipped at the moment
-    the client finished.  The ledger runs on the scheduler's clock; it is tied to the clients' CLOCK_MONOTONIC stamps
-    through the first token ever granted (requested inside the earliest first launch; the GPU is free then, so the
-    grant is immediate -- error ~1 ms on totals of seconds)."""
-    first_start = min(v[0][0] for v in spans_by_client.values() if v)
-    offset_ms = min(o["t_first"] for o in outs) * 1e3 - first_start
+    the client finished.  gem-schd counts milliseconds since its own process start on steady_clock (scheduler.cpp:97,
+    107-109) = CLOCK_MONOTONIC, the clock of the clients' stamps and of time.monotonic(): `schd_t0` is the monotonic time
+    at which the test started gem-schd (good to a few ms, on totals of seconds)."""
     out = {}
     for c, v in spans_by_client.items():
-        exit_ms = outs[c]["t_last"] * 1e3 - offset_ms
+        exit_ms = (outs[c]["t_last"] - schd_t0) * 1e3
         out[c] = sum(e - s for s, e in v[:-1]) + max(0.0, min(v[-1][1], exit_ms) - v[-1][0]) if v else 0.0
     return out, {c: len(v) for c, v in spans_by_client.items()}
 
@@ -69,12 +67,14 @@ def run_arm(which, fracs, wargs, timeout=900, extra_env=None):
         with open(os.path.join(tmp, "quota.txt"), "w") as f:
             f.write(quota)
         base = {k: v for k, v in os.environ.items() if not k.startswith("GEMHOOK_") and k not in ("LD_PRELOAD", "POD_NAME")}
-        daemons, ports, schd = [], [], None
+        daemons, ports, schd, schd_t0 = [], [], None, None
         try:
             if which != "pool":
                 sport = wp.free_port()
+                t_before = time.monotonic()
                 schd = sp.Popen([os.path.join(REF, "gem-schd-dbg"), "-p", tmp, "-f", "quota.txt", "-P", str(sport), "-q", "300", "-m", "20",
                                  "-w", "10000", "-v", "1"], cwd=tmp, stdout=sp.DEVNULL, stderr=sp.DEVNULL)
+                schd_t0 = 0.5 * (t_before + time.monotonic()) + 0.001   # its static initialisers run ~1 ms after exec
                 daemons.append(schd)
                 time.sleep(0.5)
                 for i in range(n):
@@ -125,6 +125,8 @@ def run_arm(which, fracs, wargs, timeout=900, extra_env=None):
                 for e in json.load(open(dumps[0])):
                     spans[int(e["container"].rsplit("c", 1)[1])].append((e["start"] * 1e3, e["end"] * 1e3))
             trace = [json.loads(l) for f in sorted(glob.glob(os.path.join(tmp, "trace.*.jsonl"))) for l in open(f)]
+            if schd_t0 is not None:
+                spans["schd_t0"] = schd_t0
             return spans, outs, stats(tmp), trace
         finally:
             for d in daemons:
@@ -142,7 +144,7 @@ def _three_arms(fracs, wargs):
         if acc is not None:   # pool: a client hands its token back at exit, so the ledger entry already ends there
             delivered, tokens = acc, {c: None for c in acc}
         else:
-            delivered, tokens = _delivered(spans, outs)
+            delivered, tokens = _delivered(spans, outs, spans.pop("schd_t0"))
         res[which] = {"delivered_ms": delivered, "tokens": tokens, "wall_s": [round(o["wall_s"], 3) for o in outs],
                       "launches": [o["launches"] for o in outs]}
     print("ledgers:", json.dumps(res))
