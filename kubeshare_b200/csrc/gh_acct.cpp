@@ -81,6 +81,7 @@ struct gemhook_acct {
   mem_mirror mm = {0, 0, 0};
   bool small_enabled = true;
   std::atomic<uint64_t> kernel_launches{0};
+  std::atomic<uint64_t> reduce_launches{0};  // each publishes one epoch of the totals page
   pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
 };
 
@@ -217,8 +218,10 @@ static int launch_reduce(gemhook_acct* a, CUdeviceptr d_rec, size_t n) {
     CU_TRY(GH_CALL(cuLaunchKernel, a->f_reduce, grid, 1, 1, a->warps * 32u, 1, 1, a->smem_bytes, a->stream, args, nullptr));
   }
   a->kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  a->reduce_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
+uint64_t gh_acct_reduce_launches(const gemhook_acct* a) { return a ? a->reduce_launches.load(std::memory_order_relaxed) : 0; }
 
 // ---- gpu_mem mirror -----------------------------------------------------------------------------------------------
 // The authoritative counter is the CAS word in the shared-pinned credit pool (gh_pool.cpp SlotShared); the process

@@ -26,6 +26,7 @@
 
 int gh_rpc(gemhook_request* req, gemhook_response* rsp);
 int gh_acct_push_async(gemhook_acct* a, const gemhook_record* pinned_records, size_t n);
+uint64_t gh_acct_reduce_launches(const gemhook_acct* a);
 void gh_pool_add_usage(gemhook_pool* p, int slot, uint64_t gpu_ns, uint64_t launches);
 void* gh_pool_region(gemhook_pool* p, size_t* bytes);
 
@@ -169,10 +170,13 @@ static bool stream_capturing(CUstream s, bool launch_path = false) {
 
 // device totals -> pool slot, as deltas (several processes of one pod add into the same slot).  The totals page is
 // read without any CUDA call; it reflects every reduce kernel that has completed.  Caller holds L->mu.
-static void publish_usage_locked(gh_live* L) {
+static void publish_usage_locked(gh_live* L, bool force = false) {
   if (!L->acct || !L->pool) return;
+  // every reduce launch publishes exactly one epoch: when the last epoch seen equals the number of reduce launches issued,
+  // nothing can have changed (one relaxed load instead of a walk over the page at every synchronising call)
+  if (!force && L->pub_epoch == gh_acct_reduce_launches(L->acct)) return;
   uint64_t tot[GEMHOOK_MAX_SLOTS * 3], ep = 0;
-  if (gemhook_acct_read_totals(L->acct, tot, &ep) != 0 || ep == L->pub_epoch) return;
+  if (gemhook_acct_read_totals(L->acct, tot, &ep) != 0 || ep == L->pub_epoch) return;  // (kernel still running: look again)
   uint64_t ns = tot[L->slot * 3], la = tot[L->slot * 3 + 1];
   gh_pool_add_usage(L->pool, L->slot, ns - L->pub_ns, la - L->pub_launches);
   L->pub_epoch = ep;
@@ -323,11 +327,10 @@ static void flush_stage_locked(gh_live* L, bool force) {
 // Returns false when the launches that follow are NOT covered by an accounting segment (their stream is being
 // captured, or the marker could not be recorded): the caller then keeps the gate closed, so the next launch comes
 // through here again instead of running unaccounted on the fast path.
-static bool seg_begin_locked(gh_live* L, CUstream stream) {
+static bool seg_begin_locked(gh_live* L, CUstream stream, int64_t now) {
   if (gh_cfg.dry_run || !L->cuda_ready) return true;
   // events are a ring: never re-record one that an unresolved segment still refers to
   if (L->npending > SEG_EVENTS / 2) resolve_pending_locked(L, true);
-  int64_t now = gh_now_ns();
   if (L->seg_open && L->seg_spans_sync) {  // the running segment continues across the sync we just passed
     if (L->seg_sync_return_ns && now > L->seg_sync_return_ns) L->seg_idle_ns += (uint64_t)(now - L->seg_sync_return_ns);
     L->seg_spans_sync = false;
@@ -495,8 +498,8 @@ static void host_sync_locked(gh_live* L, int64_t now) {
 void gh_host_sync_post(void) {
   gh_live* L = gh_live_get();
   if (!L || !L->enabled) return;
-  L->host_syncs.fetch_add(1, std::memory_order_relaxed);
   pthread_mutex_lock(&L->mu);
+  L->host_syncs.store(L->host_syncs.load(std::memory_order_relaxed) + 1, std::memory_order_relaxed);  // (under mu: no lock prefix)
   L->last_sync_ns = gh_now_ns();
   host_sync_locked(L, L->last_sync_ns);  // nothing else here: the GPU is idle until the next launch arrives
   bool yield = false;
@@ -644,8 +647,8 @@ static void cuda_init_locked(gh_live* L) {
 void gh_launch_slow(CUstream stream) {
   gh_live* L = gh_live_get();
   if (!L || !L->enabled) return;
-  L->slow_path.fetch_add(1, std::memory_order_relaxed);
   pthread_mutex_lock(&L->mu);
+  L->slow_path.store(L->slow_path.load(std::memory_order_relaxed) + 1, std::memory_order_relaxed);
   while (L->renewing) pthread_cond_wait(&L->renew_cv, &L->mu);
   cuda_init_locked(L);
   while (L->renewing) pthread_cond_wait(&L->renew_cv, &L->mu);
@@ -694,10 +697,10 @@ void gh_launch_slow(CUstream stream) {
     L->renewing = false;
     pthread_cond_broadcast(&L->renew_cv);
   }
-  gemhook_gate_launch_end(L->gate, gh_now_ns());
+  gemhook_gate_launch_end(L->gate, now);  // (`now` was re-read after a renewal; otherwise it is a few tens of ns old)
   // (while a capture is going on the gate stays closed: a capture is short, and the first launch after it must open a
   //  segment -- measured on the box: with the gate left open the graph replays that followed ran unaccounted)
-  if (seg_begin_locked(L, stream)) gh_gate_set(1u);
+  if (seg_begin_locked(L, stream, now)) gh_gate_set(1u);
   pthread_mutex_unlock(&L->mu);
 }
 
@@ -714,7 +717,7 @@ GH_EXPORT int gemhook_flush(void) {
   }
   resolve_pending_locked(L, true);
   flush_stage_locked(L, true);
-  publish_usage_locked(L);
+  publish_usage_locked(L, true);
   pthread_mutex_unlock(&L->mu);
   return 0;
 }

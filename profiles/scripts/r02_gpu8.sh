@@ -22,3 +22,5 @@ python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_detail_ours_storm_n1.json"))
 PY
+timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_hook.py -m gpu -q -s 2>&1 | tail -40 > gpurun_out/r02h_pytest.log
+grep -E "passed|failed|^ledgers|F?ledgers|Error|assert " gpurun_out/r02h_pytest.log | cut -c1-900
