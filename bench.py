@@ -212,14 +212,22 @@ def ledger_split_from_dump(path, nclients):
 
 
 def pool_ledger_split(pool_path, nclients):
+    """-> (per-client token ms over the full history, hand-over gaps in the ledger window: count / total ms / longest ms)"""
+    import ctypes as C
+
     import kubeshare_b200 as kb
 
     L = kb.lib()
     p = L.gemhook_pool_open(pool_path.encode(), 0, 0, 0, 0, 0)
     if not p:
-        return None
+        return None, None
     try:
-        return [L.gemhook_pool_accumulated_ms(p, L.gemhook_pool_find(p, ("bench/c%d" % i).encode())) for i in range(nclients)]
+        acc = [L.gemhook_pool_accumulated_ms(p, L.gemhook_pool_find(p, ("bench/c%d" % i).encode())) for i in range(nclients)]
+        k = L.gemhook_pool_history(p, None, None, None, 0)
+        sl, a, b = (C.c_int * k)(), (C.c_double * k)(), (C.c_double * k)()
+        k = min(k, L.gemhook_pool_history(p, sl, a, b, k))
+        gaps = [a[i + 1] - b[i] for i in range(k - 1) if a[i + 1] > b[i]]
+        return acc, {"tokens": k, "gaps": len(gaps), "gap_ms_total": round(sum(gaps), 3), "gap_ms_max": round(max(gaps), 3) if gaps else 0.0}
     finally:
         L.gemhook_pool_close(p)
 
@@ -286,7 +294,7 @@ def run_clients(workload, nclients, steps, warmup, gpu, mode, core_base, step_la
         if errs:
             raise RuntimeError("%s clients failed: %s" % (mode, errs))
         res = [json.load(open(os.path.join(tmp, "out.%d.json" % i))) for i in range(nclients)]
-        stats, ledger = [], None
+        stats, ledger, gaps = [], None, None
         if mode == "ours":
             for i in range(nclients):
                 try:
@@ -294,7 +302,7 @@ def run_clients(workload, nclients, steps, warmup, gpu, mode, core_base, step_la
                 except (OSError, ValueError):
                     stats.append({})
             try:
-                ledger = pool_ledger_split(os.path.join(tmp, "pool"), nclients)
+                ledger, gaps = pool_ledger_split(os.path.join(tmp, "pool"), nclients)
             except Exception as e:  # noqa: BLE001 -- a diagnostic, never fatal
                 log("pool ledger unavailable: %r" % (e,))
         elif dbg and schd is not None:
@@ -317,7 +325,7 @@ def run_clients(workload, nclients, steps, warmup, gpu, mode, core_base, step_la
                 "step_s": [r.get("step_s") for r in res],
                 "launches_per_s_device": launches / dev_s, "launches_per_s_host": launches / host_s,
                 "per_client_wall_s": [r["wall_s"] for r in res], "per_client_launches": [r["launches"] for r in res],
-                "stats": stats, "ledger_ms": ledger, "window": (wall0, wall1)}
+                "stats": stats, "ledger_ms": ledger, "ledger_gaps": gaps, "window": (wall0, wall1)}
     finally:
         for d in daemons:
             if d.poll() is None:
@@ -588,8 +596,8 @@ def main():
 
     # ---- gather replicas: per client count and arm, per repetition, (launches, device_s, host_s) of every replica
     def slim(rr):
-        return [{k: r[k] for k in ("launches", "device_s", "host_s", "stats", "ledger_ms", "fracs", "per_client_wall_s",
-                                   "per_client_launches")} for r in rr]
+        return [{k: r.get(k) for k in ("launches", "device_s", "host_s", "stats", "ledger_ms", "ledger_gaps", "fracs", "per_client_wall_s",
+                                       "per_client_launches", "step_s")} for r in rr]
 
     mine = {c: {which: [slim(rr) for rr in reps] for which, reps in runs.items()} for c, runs in results.items()}
     allr = [mine]
@@ -657,6 +665,8 @@ def main():
         line["jain_fairness"] = {"value": round(jf, 5), "of": how}
     if head_runs[0].get("ledger_ms"):
         line["ledger_ms"] = [round(v, 3) for v in head_runs[0]["ledger_ms"]]
+    if head_runs[0].get("ledger_gaps"):
+        line["ledger_gaps"] = head_runs[0]["ledger_gaps"]  # time between one token's end and the next one's start (last 10 s)
     if mode == "ours":
         line["hook_summary"] = summarise_stats(stats)
         peaks = measured_peaks()
