@@ -33,26 +33,57 @@ void* gh_pool_region(gemhook_pool* p, size_t* bytes);
 void gh_mem_local(uint64_t* free_b, uint64_t* total_b);  // like gh_mem_info, but never an RPC (gh_mem.cpp)
 
 uint32_t gh_gate_open = 0;  // accessed with relaxed __atomic builtins only (plain MOVs on x86, race-free by the book)
-uint32_t gh_gate_fast = 0;
-__thread gh_thread_node* gh_tl_node __attribute__((tls_model("initial-exec"))) = nullptr;
-static gh_thread_node* g_thread_nodes = nullptr;  // lock-free push-only list
+gh_hot_line gh_hot = {0u, 0xffffffffu, 0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+__thread gh_tl_state gh_tl __attribute__((tls_model("initial-exec"), aligned(16))) = {0, 0};
 
-gh_thread_node* gh_thread_register(void) {
-  gh_thread_node* nd = gh_tl_node;
-  if (nd) return nd;
-  nd = (gh_thread_node*)calloc(1, sizeof(gh_thread_node));
-  if (!nd) return nullptr;
-  gh_thread_node* head = __atomic_load_n(&g_thread_nodes, __ATOMIC_ACQUIRE);
-  do {
-    nd->next = head;
-  } while (!__atomic_compare_exchange_n(&g_thread_nodes, &head, nd, false, __ATOMIC_RELEASE, __ATOMIC_ACQUIRE));
-  gh_tl_node = nd;
-  return nd;
+// registry of the live threads' counters + the total of the threads that are gone
+static pthread_mutex_t g_thr_mu = PTHREAD_MUTEX_INITIALIZER;
+static uint64_t** g_thr_addr = nullptr;
+static size_t g_thr_n = 0, g_thr_cap = 0;
+static uint64_t g_thr_dead_total = 0;
+static pthread_key_t g_thr_key;
+static pthread_once_t g_thr_key_once = PTHREAD_ONCE_INIT;
+
+static void thread_gone(void* p) {  // pthread_key destructor: fold the leaving thread's count into the total
+  uint64_t* addr = (uint64_t*)p;
+  pthread_mutex_lock(&g_thr_mu);
+  for (size_t i = 0; i < g_thr_n; i++)
+    if (g_thr_addr[i] == addr) {
+      g_thr_dead_total += __atomic_load_n(addr, __ATOMIC_RELAXED);
+      g_thr_addr[i] = g_thr_addr[--g_thr_n];
+      break;
+    }
+  pthread_mutex_unlock(&g_thr_mu);
+}
+static void thread_key_init(void) {
+  pthread_key_create(&g_thr_key, thread_gone);
+  // initial-exec TLS: the variable sits at the same offset from the thread pointer in every thread
+  gh_hot.tls_off = (int64_t)((char*)&gh_tl - (char*)__builtin_thread_pointer());
+}
+void gh_thread_register(void) {
+  if (gh_tl.registered) return;
+  pthread_once(&g_thr_key_once, thread_key_init);
+  pthread_mutex_lock(&g_thr_mu);
+  if (g_thr_n == g_thr_cap) {
+    size_t nc = g_thr_cap ? g_thr_cap * 2 : 16;
+    uint64_t** na = (uint64_t**)realloc(g_thr_addr, nc * sizeof(uint64_t*));
+    if (na) {
+      g_thr_addr = na;
+      g_thr_cap = nc;
+    }
+  }
+  if (g_thr_n < g_thr_cap) {
+    g_thr_addr[g_thr_n++] = &gh_tl.count;
+    pthread_setspecific(g_thr_key, &gh_tl.count);
+    gh_tl.registered = 1;
+  }
+  pthread_mutex_unlock(&g_thr_mu);
 }
 uint64_t gh_total_launches(void) {
-  uint64_t n = 0;
-  for (gh_thread_node* nd = __atomic_load_n(&g_thread_nodes, __ATOMIC_ACQUIRE); nd; nd = nd->next)
-    n += __atomic_load_n(&nd->count, __ATOMIC_RELAXED);
+  pthread_mutex_lock(&g_thr_mu);
+  uint64_t n = g_thr_dead_total;
+  for (size_t i = 0; i < g_thr_n; i++) n += __atomic_load_n(g_thr_addr[i], __ATOMIC_RELAXED);
+  pthread_mutex_unlock(&g_thr_mu);
   return n;
 }
 void gh_gate_set(uint32_t open) {
@@ -60,7 +91,6 @@ void gh_gate_set(uint32_t open) {
   // with CU_HOOK_DEBUG every launch goes through the counting slow wrapper, so the fast word stays 0
   __atomic_store_n(&gh_gate_fast, (open && !__atomic_load_n(&gh_hook_debug, __ATOMIC_RELAXED)) ? 1u : 0u, __ATOMIC_RELAXED);
 }
-uint32_t gh_seg_mask = 0xffffffffu;
 
 namespace {
 const int SEG_EVENTS = 64;

@@ -78,20 +78,31 @@ void gh_host_sync_pre(void);
 void gh_host_sync_post(void);
 extern uint32_t gh_gate_open;              // 1: burst ongoing, token valid, segment open (logical gate; relaxed atomics)
 #define GH_HIDDEN __attribute__((visibility("hidden")))  /* referenced rip-relative from the assembly fast path */
-extern GH_HIDDEN uint32_t gh_gate_fast;    // gh_gate_open && !CU_HOOK_DEBUG: the ONE word the per-launch fast path tests
-// per-thread launch counters: the fast path increments its own thread's node with plain moves (no lock prefix, no
-// shared cache line); readers sum the nodes.  Nodes live for the life of the process.
-struct gh_thread_node {
-  uint64_t count;
-  gh_thread_node* next;
-  char pad[48];
+// Everything the per-launch fast path reads lives in ONE cache line (the driver's own launch path runs ~2 us between two
+// launches and evicts L1: measured on a host-bound box, every extra line the hook touched cost ~5 ns = 0.25 %), plus the
+// launching thread's own TLS line.
+enum { GH_FN_LAUNCH = 0, GH_FN_COOP, GH_FN_LAUNCH_PTSZ, GH_FN_COOP_PTSZ, GH_FN_LAUNCHEX, GH_FN_LAUNCHEX_PTSZ, GH_FN_COUNT };
+struct alignas(64) gh_hot_line {
+  uint32_t gate_fast;   // +0   gh_gate_open && !CU_HOOK_DEBUG: the ONE word the fast path tests
+  uint32_t seg_mask;    // +4   segment every (mask+1) launches; 0xffffffff = burst edges only
+  int64_t tls_off;      // +8   offset of gh_tl from the thread pointer (initial-exec TLS: the same in every thread)
+  void* fn[GH_FN_COUNT];  // +16  resolved driver entry points of the six kernel-launch hooks
 };
-extern GH_HIDDEN __thread gh_thread_node* gh_tl_node __attribute__((tls_model("initial-exec")));
-gh_thread_node* gh_thread_register(void);  // this thread's node (creates it on first use)
+static_assert(sizeof(gh_hot_line) == 64, "one cache line");
+extern GH_HIDDEN gh_hot_line gh_hot;
+#define gh_gate_fast (gh_hot.gate_fast)
+#define gh_seg_mask (gh_hot.seg_mask)
+// per-thread launch counter: incremented by its own thread with plain moves (no lock prefix, no shared line); readers
+// sum the registered threads' counters (slow path only)
+struct gh_tl_state {
+  uint64_t count;
+  uint64_t registered;  // 0 until the thread's first slow path has put &count into the registry
+};
+extern GH_HIDDEN __thread gh_tl_state gh_tl __attribute__((tls_model("initial-exec"), aligned(16)));
+void gh_thread_register(void);             // idempotent; called on this thread's first slow path
 uint64_t gh_total_launches(void);          // sum over all threads that ever launched
 void gh_gate_set(uint32_t open);           // set the logical gate (and the fast word derived from it)
 extern uint32_t gh_hook_debug;            // CU_HOOK_DEBUG=1: count calls per symbol (relaxed atomics; set once by the config load)
-extern GH_HIDDEN uint32_t gh_seg_mask;               // segment every (mask+1) launches; 0xffffffff = burst edges only
 void gh_segment_tick(CUstream stream);
 void gh_stream_destroyed(CUstream stream);  // cuStreamDestroy pre-hook: a segment open on that stream is closed first
 

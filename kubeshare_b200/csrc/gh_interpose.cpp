@@ -64,25 +64,23 @@ static void* resolve_late(void** slot, const char* name) {
 // FAST PATH, shaped by hand because it decides the overhead where the launch storm is host-bound (measured on one of
 // the pool's boxes: 2.01 us per launch un-hooked, so every 20 ns of hook is 1 %).  A launch hook is a leaf that either
 // tail-jumps into the driver with its arguments untouched, or tail-jumps into a same-signature slow twin:
-//     load gh_gate_fast, load this thread's counter node (initial-exec TLS), plain increment, mask test, jmp.
+//     load the driver entry + gh_gate_fast (one cache line), plain increment of the thread's TLS counter, mask test, jmp.
 // No lock prefix (round 1: lock xadd on a shared counter), no register saves (round 1: six pushes and five stack
 // reloads, because the slow-path call sat in the same function).
-static inline __attribute__((always_inline)) bool launch_fast_ok(void) {
-  gh_thread_node* nd = gh_tl_node;
-  if (__builtin_expect(!__atomic_load_n(&gh_gate_fast, __ATOMIC_RELAXED) || !nd, 0)) return false;
-  uint64_t n = nd->count + 1;
+static inline __attribute__((always_inline)) bool launch_fast_ok(void) {  // (C twin of the assembly below, other ISAs)
+  if (__builtin_expect(!__atomic_load_n(&gh_gate_fast, __ATOMIC_RELAXED) || !gh_tl.registered, 0)) return false;
+  uint64_t n = gh_tl.count + 1;
   if (__builtin_expect(((uint32_t)n & gh_seg_mask) == 0, 0)) return false;  // segment tick due: slow twin
-  __atomic_store_n(&nd->count, n, __ATOMIC_RELAXED);
+  __atomic_store_n(&gh_tl.count, n, __ATOMIC_RELAXED);
   return true;
 }
 // everything else: gate closed (burst edge / token), first launch of a thread, CU_HOOK_DEBUG counting, segment tick
 static __attribute__((noinline)) void launch_slow_common(CUstream hStream, int counter) {
   if (__atomic_load_n(&gh_hook_debug, __ATOMIC_RELAXED)) __atomic_add_fetch(&g_calls[counter], 1, __ATOMIC_RELAXED);
-  gh_thread_node* nd = gh_thread_register();
+  gh_thread_register();
   if (__atomic_load_n(&gh_gate_open, __ATOMIC_RELAXED) == 0) gh_launch_slow(hStream);
-  if (!nd) return;
-  uint64_t n = nd->count + 1;
-  __atomic_store_n(&nd->count, n, __ATOMIC_RELAXED);
+  uint64_t n = gh_tl.count + 1;
+  __atomic_store_n(&gh_tl.count, n, __ATOMIC_RELAXED);
   if (((uint32_t)n & gh_seg_mask) == 0 && __atomic_load_n(&gh_gate_open, __ATOMIC_RELAXED)) gh_segment_tick(hStream);
 }
 
@@ -103,55 +101,58 @@ static void *p_graphlaunch, *p_graphlaunch_pt;
 // The slow twin has the hook's exact signature, so both exits of the hook are plain jumps.  On x86-64 the hook itself
 // is written in assembly: left to the compiler the "leaf with two tail calls" still saved six registers and copied the
 // five stack arguments to registers and back (it needs scratch registers and does not see that the outgoing stack
-// arguments ARE the incoming ones).  13 instructions, scratch registers rax/r10/r11 only (never argument registers):
-//     real = gh_fastfn_<hook>; gate = gh_gate_fast; node = %fs:gh_tl_node; n = node->count + 1;
-//     if (!real || !gate || !node || !(n & gh_seg_mask)) jmp <hook>_slowtwin;  node->count = n;  jmp *real
+// arguments ARE the incoming ones).  12 instructions, scratch registers rax/r10/r11 only (never argument registers),
+// two cache lines (gh_hot and the thread's TLS line):
+//     real = gh_hot.fn[i]; if (!real || !gh_hot.gate_fast) slow;  tl = %fs + gh_hot.tls_off;
+//     if (!tl->registered) slow;  n = tl->count + 1;  if (!(n & gh_hot.seg_mask)) slow;  tl->count = n;  jmp *real
+#define GH_STR2(x) #x
+#define GH_STR(x) GH_STR2(x)
 #if defined(__x86_64__) && !defined(GEMHOOK_NO_ASM_FASTPATH)
-#define GH_LAUNCH_ENTRY(name, fn_t, params, args)                                                               \
-  extern "C" {                                                                                                 \
-  __attribute__((visibility("hidden"), used)) void* gh_fastfn_##name = nullptr;                                \
-  }                                                                                                            \
+#define GH_LAUNCH_ENTRY(name, fn_t, idx, params, args)                                                          \
   asm(".text\n.p2align 5\n.globl " #name "\n.type " #name ",@function\n" #name ":\n"                          \
       "  endbr64\n"                                                                                            \
-      "  movq gh_fastfn_" #name "(%rip), %rax\n"                                                               \
+      "  movq gh_hot+16+8*" GH_STR(idx) "(%rip), %rax\n"                                                       \
       "  testq %rax, %rax\n"                                                                                   \
       "  jz 1f\n"                                                                                              \
-      "  cmpl $0, gh_gate_fast(%rip)\n"                                                                        \
+      "  cmpl $0, gh_hot(%rip)\n"                                                                              \
       "  je 1f\n"                                                                                              \
-      "  movq gh_tl_node@gottpoff(%rip), %r10\n"                                                               \
-      "  movq %fs:(%r10), %r10\n"                                                                              \
-      "  testq %r10, %r10\n"                                                                                   \
-      "  jz 1f\n"                                                                                              \
-      "  movq (%r10), %r11\n"                                                                                  \
+      "  movq gh_hot+8(%rip), %r10\n"                                                                          \
+      "  cmpq $0, %fs:8(%r10)\n"                                                                               \
+      "  je 1f\n"                                                                                              \
+      "  movq %fs:(%r10), %r11\n"                                                                              \
       "  incq %r11\n"                                                                                          \
-      "  testl %r11d, gh_seg_mask(%rip)\n"                                                                     \
+      "  testl %r11d, gh_hot+4(%rip)\n"                                                                        \
       "  jz 1f\n"                                                                                              \
-      "  movq %r11, (%r10)\n"                                                                                  \
+      "  movq %r11, %fs:(%r10)\n"                                                                              \
       "  jmp *%rax\n"                                                                                          \
       "1:\n"                                                                                                   \
       "  jmp " #name "_slowtwin\n"                                                                             \
       ".size " #name ", .-" #name "\n");
-#define GH_FASTFN_PUBLISH(name, fn) __atomic_store_n(&gh_fastfn_##name, (void*)(fn), __ATOMIC_RELEASE)
 #else
-#define GH_LAUNCH_ENTRY(name, fn_t, params, args)                                                               \
-  static void* gh_fastfn_##name = nullptr;                                                                      \
+#define GH_LAUNCH_ENTRY(name, fn_t, idx, params, args)                                                          \
   GH_HOOK name params {                                                                                         \
-    fn_t real = (fn_t)__atomic_load_n(&gh_fastfn_##name, __ATOMIC_RELAXED);                                     \
+    fn_t real = (fn_t)__atomic_load_n(&gh_hot.fn[idx], __ATOMIC_RELAXED);                                       \
     if (__builtin_expect(real != nullptr && launch_fast_ok(), 1)) return real args;                             \
     return name##_slowtwin args;                                                                                \
   }
-#define GH_FASTFN_PUBLISH(name, fn) __atomic_store_n(&gh_fastfn_##name, (void*)(fn), __ATOMIC_RELEASE)
 #endif
+#define GH_FASTFN_PUBLISH(idx, ptr) __atomic_store_n(&gh_hot.fn[idx], (void*)(ptr), __ATOMIC_RELEASE)
 
-#define GH_LAUNCH_HOOK(name, fn_t, slot, symbol, counter, stream_expr, params, args)                           \
+#define GH_LAUNCH_HOOK(name, fn_t, idx, slot, symbol, counter, stream_expr, params, args)                      \
   extern "C" __attribute__((visibility("hidden"), used, noinline)) CUresult CUDAAPI name##_slowtwin params;     \
   extern "C" __attribute__((visibility("default"))) CUresult CUDAAPI name params;                               \
-  GH_LAUNCH_ENTRY(name, fn_t, params, args)                                                                     \
+  GH_LAUNCH_ENTRY(name, fn_t, idx, params, args)                                                                \
   CUresult CUDAAPI name##_slowtwin params {                                                                     \
     launch_slow_common(stream_expr, counter);                                                                   \
     fn_t real = (fn_t)LATE(slot, symbol);                                                                       \
-    GH_FASTFN_PUBLISH(name, real);                                                                              \
+    GH_FASTFN_PUBLISH(idx, real);                                                                               \
     return real args;                                                                                           \
+  }
+// hooks that are not worth a place in the hot line (one graph launch stands for many kernels): plain C, same gate
+#define GH_LAUNCH_HOOK_COLD(name, fn_t, slot, symbol, counter, stream_expr, params, args)                       \
+  GH_HOOK name params {                                                                                         \
+    launch_slow_common(stream_expr, counter);                                                                   \
+    return ((fn_t)LATE(slot, symbol))args;                                                                      \
   }
 
 #define LAUNCH_PARAMS (CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned shmem, \
@@ -163,20 +164,20 @@ static void *p_graphlaunch, *p_graphlaunch_pt;
 #define EX_PARAMS (const CUlaunchConfig* config, CUfunction f, void** params, void** extra)
 #define EX_ARGS (config, f, params, extra)
 
-GH_LAUNCH_HOOK(cuLaunchKernel, launch_fn, gh_real.cuLaunchKernel, "cuLaunchKernel", CNT_cuLaunchKernel, hStream, LAUNCH_PARAMS, LAUNCH_ARGS)
-GH_LAUNCH_HOOK(cuLaunchCooperativeKernel, coop_fn, gh_real.cuLaunchCooperativeKernel, "cuLaunchCooperativeKernel",
+GH_LAUNCH_HOOK(cuLaunchKernel, launch_fn, 0, gh_real.cuLaunchKernel, "cuLaunchKernel", CNT_cuLaunchKernel, hStream, LAUNCH_PARAMS, LAUNCH_ARGS)
+GH_LAUNCH_HOOK(cuLaunchCooperativeKernel, coop_fn, 1, gh_real.cuLaunchCooperativeKernel, "cuLaunchCooperativeKernel",
                CNT_cuLaunchCooperativeKernel, hStream, COOP_PARAMS, COOP_ARGS)
-GH_LAUNCH_HOOK(cuLaunchKernel_ptsz, launch_fn, p_launch_ptsz, "cuLaunchKernel_ptsz", CNT_cuLaunchKernel, hStream, LAUNCH_PARAMS, LAUNCH_ARGS)
-GH_LAUNCH_HOOK(cuLaunchCooperativeKernel_ptsz, coop_fn, p_coop_ptsz, "cuLaunchCooperativeKernel_ptsz", CNT_cuLaunchCooperativeKernel,
+GH_LAUNCH_HOOK(cuLaunchKernel_ptsz, launch_fn, 2, p_launch_ptsz, "cuLaunchKernel_ptsz", CNT_cuLaunchKernel, hStream, LAUNCH_PARAMS, LAUNCH_ARGS)
+GH_LAUNCH_HOOK(cuLaunchCooperativeKernel_ptsz, coop_fn, 3, p_coop_ptsz, "cuLaunchCooperativeKernel_ptsz", CNT_cuLaunchCooperativeKernel,
                hStream, COOP_PARAMS, COOP_ARGS)
-GH_LAUNCH_HOOK(cuLaunchKernelEx, launchex_fn, p_launchex, "cuLaunchKernelEx", CNT_cuLaunchKernelEx, (config ? config->hStream : nullptr),
+GH_LAUNCH_HOOK(cuLaunchKernelEx, launchex_fn, 4, p_launchex, "cuLaunchKernelEx", CNT_cuLaunchKernelEx, (config ? config->hStream : nullptr),
                EX_PARAMS, EX_ARGS)
-GH_LAUNCH_HOOK(cuLaunchKernelEx_ptsz, launchex_fn, p_launchex_ptsz, "cuLaunchKernelEx_ptsz", CNT_cuLaunchKernelEx,
+GH_LAUNCH_HOOK(cuLaunchKernelEx_ptsz, launchex_fn, 5, p_launchex_ptsz, "cuLaunchKernelEx_ptsz", CNT_cuLaunchKernelEx,
                (config ? config->hStream : nullptr), EX_PARAMS, EX_ARGS)
 // graph launches pass the token gate like a kernel launch
-GH_LAUNCH_HOOK(cuGraphLaunch, graphlaunch_fn, p_graphlaunch, "cuGraphLaunch", CNT_cuGraphLaunch, hStream, (CUgraphExec g, CUstream hStream),
+GH_LAUNCH_HOOK_COLD(cuGraphLaunch, graphlaunch_fn, p_graphlaunch, "cuGraphLaunch", CNT_cuGraphLaunch, hStream, (CUgraphExec g, CUstream hStream),
                (g, hStream))
-GH_LAUNCH_HOOK(cuGraphLaunch_ptsz, graphlaunch_fn, p_graphlaunch_pt, "cuGraphLaunch_ptsz", CNT_cuGraphLaunch, hStream,
+GH_LAUNCH_HOOK_COLD(cuGraphLaunch_ptsz, graphlaunch_fn, p_graphlaunch_pt, "cuGraphLaunch_ptsz", CNT_cuGraphLaunch, hStream,
                (CUgraphExec g, CUstream hStream), (g, hStream))
 
 // ---- gpu_mem cap ----------------------------------------------------------------------------------------

@@ -144,7 +144,10 @@ def _three_arms(fracs, wargs):
         if acc is not None:   # pool: a client hands its token back at exit, so the ledger entry already ends there
             delivered, tokens = acc, {c: None for c in acc}
         else:
-            delivered, tokens = _delivered(spans, outs, spans.pop("schd_t0"))
+            t0_ = spans.pop("schd_t0")
+            delivered, tokens = _delivered(spans, outs, t0_)
+            print("ledger %s:" % which, {c: [(round(s_), round(e_)) for s_, e_ in v] for c, v in spans.items()},
+                  "exits", [round((o["t_last"] - t0_) * 1e3) for o in outs], "first launches", [round((o["t_first"] - t0_) * 1e3) for o in outs])
         res[which] = {"delivered_ms": delivered, "tokens": tokens, "wall_s": [round(o["wall_s"], 3) for o in outs],
                       "launches": [o["launches"] for o in outs]}
     print("ledgers:", json.dumps(res))
