@@ -634,7 +634,9 @@ static void cuda_init_locked(gh_live* L) {
   GH_CALL(cuCtxGetCurrent, &L->ctx);
   if (!gh_cfg.dry_run) {
     GH_CALL(cuEventCreate, &L->ev_token, CU_EVENT_DEFAULT);
-    GH_CALL(cuEventCreate, &L->ev_drain, CU_EVENT_DEFAULT);
+    // blocking sync: the tracker thread must not spin against the launching thread while it waits for the drain (a
+    // client pinned to one CPU would lose a scheduler timeslice per token)
+    GH_CALL(cuEventCreate, &L->ev_drain, CU_EVENT_BLOCKING_SYNC);
     for (int i = 0; i < SEG_EVENTS; i++) GH_CALL(cuEventCreate, &L->seg_ev[i], CU_EVENT_DEFAULT);
     uint32_t nslots = L->pool ? (uint32_t)gemhook_pool_nslots(L->pool) : 1;
     if (nslots < 1) nslots = 1;
