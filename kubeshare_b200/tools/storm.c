@@ -102,6 +102,7 @@ static void* mt_worker(void* p) {
 int main(int argc, char** argv) {
   const char* mode = "storm";
   long step_launches = 65536, sync_every = 1024, steps = 16, warmup = 3, rounds = 2000;
+  double pace_ns = 0; /* storm mode: host-side delay added after every launch (how a slower launcher would look) */
   double spin_us = 5.0, sleep_mean_ms = 2.0;
   unsigned long long sweep_bytes = 40ULL << 30;
   const char* out_path = NULL;
@@ -113,6 +114,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--sync-every") && i + 1 < argc) sync_every = atol(argv[++i]);
     else if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atol(argv[++i]);
     else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atol(argv[++i]);
+    else if (!strcmp(argv[i], "--pace-ns") && i + 1 < argc) pace_ns = atof(argv[++i]);
     else if (!strcmp(argv[i], "--rounds") && i + 1 < argc) rounds = atol(argv[++i]);
     else if (!strcmp(argv[i], "--spin-us") && i + 1 < argc) spin_us = atof(argv[++i]);
     else if (!strcmp(argv[i], "--sleep-mean-ms") && i + 1 < argc) sleep_mean_ms = atof(argv[++i]);
@@ -158,6 +160,13 @@ int main(int argc, char** argv) {
     }
     barrier(barrier_dir, client_id, nclients, "ready");
     double* step_s = (double*)calloc((size_t)steps + 1, sizeof(double));
+    unsigned long long pace_ticks = 0;
+    if (pace_ns > 0) { /* TSC ticks per ns, over 20 ms */
+      double a = now_s();
+      unsigned long long c0 = __builtin_ia32_rdtsc();
+      while (now_s() - a < 0.02) {}
+      pace_ticks = (unsigned long long)((double)(__builtin_ia32_rdtsc() - c0) / ((now_s() - a) * 1e9) * pace_ns);
+    }
     CK(cuCtxSynchronize());
     double t0 = now_s();
     CK(cuEventRecord(e0, NULL));
@@ -165,6 +174,10 @@ int main(int argc, char** argv) {
       double ts = now_s();
       for (long i = 1; i <= step_launches; i++) {
         CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+        if (pace_ticks) {
+          unsigned long long c = __builtin_ia32_rdtsc();
+          while (__builtin_ia32_rdtsc() - c < pace_ticks) {}
+        }
         if (i % sync_every == 0) CK(cuCtxSynchronize());
       }
       CK(cuCtxSynchronize());

@@ -122,7 +122,19 @@ CUresult cuCtxGetCurrent(CUcontext* c) { *c = cur_ctx; return CUDA_SUCCESS; }
 CUresult cuCtxGetDevice(CUdevice* d) { *d = 0; return CUDA_SUCCESS; }
 CUresult cuCtxSynchronize(void) { n_sync++; wait_until(timeline()); return CUDA_SUCCESS; }
 
-CUresult cuModuleLoadData(CUmodule* m, const void* image) { n_module++; *m = (CUmodule)&fake_mod_obj; return CUDA_SUCCESS; }
+CUresult cuModuleLoadData(CUmodule* m, const void* image) {
+  /* STUB_MODULE_LOAD_US: the second and later loads (the first is the application's own module; the next one is the
+   * hook's cubin, loaded during its first-use initialisation) take this long -- a real driver needs milliseconds */
+  const char* e = getenv("STUB_MODULE_LOAD_US");
+  if (e && n_module >= 1) {
+    long us = atol(e);
+    struct timespec ts = {us / 1000000, (us % 1000000) * 1000};
+    nanosleep(&ts, NULL);
+  }
+  n_module++;
+  *m = (CUmodule)&fake_mod_obj;
+  return CUDA_SUCCESS;
+}
 CUresult cuModuleUnload(CUmodule m) { return CUDA_SUCCESS; }
 CUresult cuModuleGetFunction(CUfunction* f, CUmodule m, const char* name) {
   *f = (CUfunction)(uintptr_t)(0x1000 + (uintptr_t)strlen(name));

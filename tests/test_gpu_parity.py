@@ -90,7 +90,7 @@ def run_arm(which, fracs, wargs, timeout=900, extra_env=None):
                     e.update(LD_PRELOAD=os.path.join(REF, "libgemhook_ref.so.1"), POD_MANAGER_PORT=str(ports[i]))
                 elif which == "ours-tcp":
                     e.update(LD_PRELOAD=kb.LIB_PATH, GEMHOOK_SCHEDULER_IP="127.0.0.1", POD_MANAGER_PORT=str(ports[i]),
-                             GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"))
+                             GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"), GEMHOOK_TOKEN_TRACE=os.path.join(tmp, "trace.%d.jsonl"))
                 else:
                     e.update(LD_PRELOAD=kb.LIB_PATH, GEMHOOK_POOL=os.path.join(tmp, "pool"), GEMHOOK_QUOTA_FILE=os.path.join(tmp, "quota.txt"),
                              GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"), GEMHOOK_TOKEN_TRACE=os.path.join(tmp, "trace.%d.jsonl"))

@@ -5,6 +5,7 @@ symbol, dlsym, cuGetProcAddress), the token protocol on the wire -- against a sc
 AND against the live reference gem-pmgr + gem-schd --, the gpu_mem cap (config 4 sweep, bit-exact vs the
 oracle rule) and two co-resident clients arbitrating through the shared credit pool.
 """
+import glob
 import json
 import os
 import socket
@@ -385,3 +386,25 @@ def test_two_processes_of_one_pod_share_the_pods_token():
         st = stats_files(tmp)
         assert len(st) == 2 and all(s["launches"] == 120000 for s in st)
         assert sum(s["token_requests"] for s in st) >= 4
+
+
+def test_first_renewal_already_reports_a_doubled_burst():
+    """A client that launches without idle gaps reports 2 x its measured burst from its first renewal on
+    (estimate_full_burst, hook.cpp:402-417: the window predictor is below SCHD_OVERHEAD), so a lone tenant's quota grows
+    by the x1.5 law of gem-schd's EMA (300 -> 448 -> 671 ... on the B200 with the reference hook).  The hook's own
+    first-use initialisation -- which, unlike the reference's, runs at the first *launch*, after the application's first
+    synchronising call opened a window -- must not be mistaken for application idle time: it once sat in the window
+    predictor for 3 s and kept the estimate un-doubled (six 296 ms tokens where the reference had already reached 1 s)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        env = hooked_env(tmp, GEMHOOK_BASE_QUOTA_MS=50, GEMHOOK_MIN_QUOTA_MS=20, GEMHOOK_TOKEN_TRACE=os.path.join(tmp, "trace.%d.jsonl"),
+                         STUB_KERNEL_US=2, STUB_MODULE_LOAD_US=5000)   # a real driver loads the hook's cubin in milliseconds
+        # the application synchronises once before its first launch (warm-up 0: barrier + cuCtxSynchronize, then launches)
+        run_storm(env, "--mode", "storm", "--steps", 4, "--warmup", 0, "--step-launches", 65536, "--sync-every", 1024)
+        tr = [json.loads(l) for f in glob.glob(os.path.join(tmp, "trace.*.jsonl")) for l in open(f)]
+        assert len(tr) >= 4, tr
+        # request 0: initialisation (burst 0); request 1: first launch (burst 0); request 2: after the first token was used up
+        assert tr[0]["burst_ms"] == 0 and tr[1]["burst_ms"] == 0
+        first = tr[2]
+        assert 1.8 * 50 <= first["burst_ms"] <= 2.05 * 50, tr[:4]      # 2 x (a 50 ms token's worth of launches)
+        assert first["quota_ms"] == pytest.approx(0.5 * first["burst_ms"] + 0.5 * 50, rel=1e-9)   # get_quota, scheduler.cpp:84-97
+        assert tr[3]["burst_ms"] > first["burst_ms"]
