@@ -102,6 +102,7 @@ static void* mt_worker(void* p) {
 int main(int argc, char** argv) {
   const char* mode = "storm";
   long step_launches = 65536, sync_every = 1024, steps = 16, warmup = 3, rounds = 2000;
+  int track_blocked = 0; /* storm mode: time every driver call (rdtsc); calls longer than 5 ms are "blocked" (token waits) */
   double pace_ns = 0; /* storm mode: host-side delay added after every launch (how a slower launcher would look) */
   double spin_us = 5.0, sleep_mean_ms = 2.0;
   unsigned long long sweep_bytes = 40ULL << 30;
@@ -115,6 +116,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atol(argv[++i]);
     else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atol(argv[++i]);
     else if (!strcmp(argv[i], "--pace-ns") && i + 1 < argc) pace_ns = atof(argv[++i]);
+    else if (!strcmp(argv[i], "--track-blocked")) track_blocked = 1;
     else if (!strcmp(argv[i], "--rounds") && i + 1 < argc) rounds = atol(argv[++i]);
     else if (!strcmp(argv[i], "--spin-us") && i + 1 < argc) spin_us = atof(argv[++i]);
     else if (!strcmp(argv[i], "--sleep-mean-ms") && i + 1 < argc) sleep_mean_ms = atof(argv[++i]);
@@ -160,29 +162,46 @@ int main(int argc, char** argv) {
     }
     barrier(barrier_dir, client_id, nclients, "ready");
     double* step_s = (double*)calloc((size_t)steps + 1, sizeof(double));
-    unsigned long long pace_ticks = 0;
-    if (pace_ns > 0) { /* TSC ticks per ns, over 20 ms */
+    unsigned long long pace_ticks = 0, blocked_thr = 0, blocked_ticks = 0;
+    double ticks_per_ns = 0;
+    if (pace_ns > 0 || track_blocked) { /* TSC ticks per ns, over 20 ms */
       double a = now_s();
       unsigned long long c0 = __builtin_ia32_rdtsc();
       while (now_s() - a < 0.02) {}
-      pace_ticks = (unsigned long long)((double)(__builtin_ia32_rdtsc() - c0) / ((now_s() - a) * 1e9) * pace_ns);
+      ticks_per_ns = (double)(__builtin_ia32_rdtsc() - c0) / ((now_s() - a) * 1e9);
+      pace_ticks = (unsigned long long)(ticks_per_ns * pace_ns);
+      blocked_thr = (unsigned long long)(ticks_per_ns * 5e6);
     }
-    CK(cuCtxSynchronize());
+    /* a hooked call that takes longer than 5 ms waited for a token (a launch costs ~2 us, draining 1024 noops ~2 ms):
+     * what is left of the client's run time after those calls is the time it really had the GPU */
+#define TRACKED(call)                                             \
+  do {                                                            \
+    if (track_blocked) {                                          \
+      unsigned long long c_ = __builtin_ia32_rdtsc();             \
+      CK(call);                                                   \
+      unsigned long long d_ = __builtin_ia32_rdtsc() - c_;        \
+      if (d_ > blocked_thr) blocked_ticks += d_;                  \
+    } else {                                                      \
+      CK(call);                                                   \
+    }                                                             \
+  } while (0)
+    TRACKED(cuCtxSynchronize());
     double t0 = now_s();
     CK(cuEventRecord(e0, NULL));
     for (long s = 0; s < steps; s++) {
       double ts = now_s();
       for (long i = 1; i <= step_launches; i++) {
-        CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+        TRACKED(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
         if (pace_ticks) {
           unsigned long long c = __builtin_ia32_rdtsc();
           while (__builtin_ia32_rdtsc() - c < pace_ticks) {}
         }
-        if (i % sync_every == 0) CK(cuCtxSynchronize());
+        if (i % sync_every == 0) CK(cuCtxSynchronize()); /* never a token wait: tokens are asked for at launches */
       }
       CK(cuCtxSynchronize());
       step_s[s] = now_s() - ts;
     }
+#undef TRACKED
     CK(cuEventRecord(e1, NULL));
     CK(cuEventSynchronize(e1));
     double t1 = now_s();
@@ -191,8 +210,9 @@ int main(int argc, char** argv) {
     fprintf(out,
             "{\"mode\": \"storm\", \"client\": %d, \"launches\": %ld, \"steps\": %ld, \"warmup\": %ld, "
             "\"step_launches\": %ld, \"sync_every\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f, \"t0\": %.9f, "
-            "\"t1\": %.9f, \"t_first\": %.9f, \"t_last\": %.9f, \"step_s\": [",
-            client_id, steps * step_launches, steps, warmup, step_launches, sync_every, t1 - t0, ev_ms, t0, t1, t_first, t1);
+            "\"t1\": %.9f, \"t_first\": %.9f, \"t_last\": %.9f, \"blocked_s\": %.9f, \"step_s\": [",
+            client_id, steps * step_launches, steps, warmup, step_launches, sync_every, t1 - t0, ev_ms, t0, t1, t_first, t1,
+            ticks_per_ns > 0 ? (double)blocked_ticks / ticks_per_ns / 1e9 : 0.0);
     for (long s = 0; s < steps; s++) fprintf(out, "%s%.9f", s ? ", " : "", step_s[s]);
     fprintf(out, "]}\n");
   } else if (!strcmp(mode, "bursty")) {
