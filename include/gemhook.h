@@ -165,6 +165,9 @@ int gemhook_pool_schedule(gemhook_pool *, double now_ms, int *slot_out, double *
 double gemhook_pool_usage(gemhook_pool *, int slot, double now_ms);
 size_t gemhook_pool_history(const gemhook_pool *, int *slots, double *starts, double *ends, size_t cap);
 double gemhook_pool_accumulated_ms(const gemhook_pool *, int slot);
+/* the pool's clock right now: ms since the pool file was created, on CLOCK_MONOTONIC -- the time base of the ledger
+ * (gem-schd's ms_since_start, scheduler.cpp:107-109); lets a reader place ledger entries on its own clock. */
+double gemhook_pool_now_ms(const gemhook_pool *);
 /* blocking convenience used by the live hook: post request, arbitrate, wait for the grant. */
 double gemhook_pool_acquire(gemhook_pool *, int slot, double overuse_ms, double burst_ms);
 /* same; *forwarded (optional) = 1 if the request went to the scheduler policy (the reply is the client's new adaptive

@@ -91,6 +91,7 @@ def lib():
         "gemhook_pool_usage": (d, [vp, C.c_int, d]),
         "gemhook_pool_history": (sz, [vp, pi, pd, pd, sz]),
         "gemhook_pool_accumulated_ms": (d, [vp, C.c_int]),
+        "gemhook_pool_now_ms": (d, [vp]),
         "gemhook_pool_acquire": (d, [vp, C.c_int, d, d]),
         "gemhook_pool_acquire_ex": (d, [vp, C.c_int, d, d, pi]),
         "gemhook_pool_release": (None, [vp, C.c_int]),

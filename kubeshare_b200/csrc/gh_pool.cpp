@@ -1008,6 +1008,8 @@ GH_EXPORT size_t gemhook_pool_history(const gemhook_pool* cp, int* slots, double
   });
 }
 
+GH_EXPORT double gemhook_pool_now_ms(const gemhook_pool* p) { return p ? p->now_ms() : 0.0; }
+
 GH_EXPORT double gemhook_pool_accumulated_ms(const gemhook_pool* cp, int slot) {
   if (slot < 0 || slot >= GEMHOOK_MAX_SLOTS) return 0.0;
   return observe(cp, [&](const State& s) {

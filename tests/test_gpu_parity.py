@@ -112,6 +112,7 @@ def run_arm(which, fracs, wargs, timeout=900, extra_env=None):
                 L.gemhook_pool_history(p, sl, a, b, k)
                 names = {L.gemhook_pool_find(p, ("bench/c%d" % i).encode()): i for i in range(n)}
                 acc = {i: L.gemhook_pool_accumulated_ms(p, s_) for s_, i in names.items()}
+                schd_t0 = time.monotonic() - L.gemhook_pool_now_ms(p) / 1e3   # the pool ledger's origin on CLOCK_MONOTONIC
                 L.gemhook_pool_close(p)
                 for j in range(k):
                     spans[names[sl[j]]].append((a[j], b[j]))
@@ -141,10 +142,18 @@ def _three_arms(fracs, wargs):
     for which in ("reference", "ours-tcp", "pool"):
         spans, outs, st, _ = run_arm(which, fracs, wargs)
         acc = spans.pop("accumulated_ms", None)
-        if acc is not None:   # pool: a client hands its token back at exit, so the ledger entry already ends there
-            delivered, tokens = acc, {c: None for c in acc}
+        t0_ = spans.pop("schd_t0")
+        if acc is not None:
+            # pool: a client hands its token back when its process exits -- after its own end stamp by however long the
+            # teardown (context destroy, with peers still running) takes.  Same clipping as for the gem-schd ledgers: the
+            # part of the client's last entry that lies after its own end stamp is not token time "while it ran".
+            delivered, tokens = {}, {c: None for c in acc}
+            for c in acc:
+                exit_ms = (outs[c]["t_last"] - t0_) * 1e3
+                over = max(0.0, spans[c][-1][1] - max(exit_ms, spans[c][-1][0])) if spans[c] else 0.0
+                delivered[c] = acc[c] - over
+            print("ledger pool: overhang after the client's own end", {c: round(acc[c] - delivered[c], 1) for c in acc})
         else:
-            t0_ = spans.pop("schd_t0")
             delivered, tokens = _delivered(spans, outs, t0_)
             print("ledger %s:" % which, {c: [(round(s_), round(e_)) for s_, e_ in v] for c, v in spans.items()},
                   "exits", [round((o["t_last"] - t0_) * 1e3) for o in outs], "first launches", [round((o["t_first"] - t0_) * 1e3) for o in outs])
