@@ -687,11 +687,14 @@ void gh_launch_slow(CUstream stream) {
   // allocations, the first token -- up to a whole quota when a peer holds the GPU) is not application idle time: the
   // predictors see this launch at the moment it was issued, or the span would sit in the window predictor for its whole
   // validity and switch off the burst doubling of estimate_full_burst (hook.cpp:412) for the first seconds of the run.
-  const bool first_use = !L->cuda_ready;
-  const int64_t t_issue = gh_now_ns();
-  cuda_init_locked(L);
-  while (L->renewing) pthread_cond_wait(&L->renew_cv, &L->mu);
-  int64_t now = first_use ? t_issue : gh_now_ns();
+  int64_t now;
+  if (!L->cuda_ready) {
+    now = gh_now_ns();
+    cuda_init_locked(L);
+    while (L->renewing) pthread_cond_wait(&L->renew_cv, &L->mu);
+  } else {
+    now = gh_now_ns();
+  }
   if (L->last_sync_ns) {  // the application's most recent idle gap: decides whether yielding at syncs pays off
     L->last_window_ms = (double)(now - L->last_sync_ns) / 1e6;
     L->last_sync_ns = 0;

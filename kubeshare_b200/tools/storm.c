@@ -108,6 +108,9 @@ int main(int argc, char** argv) {
   unsigned long long sweep_bytes = 40ULL << 30;
   const char* out_path = NULL;
   const char* barrier_dir = NULL;
+  /* a barrier BEFORE the first call a hook could intercept (after context creation and module load): co-resident clients
+   * do not create contexts -- which stalls the device for everybody -- while a peer already runs on a token */
+  const char* start_barrier_dir = NULL;
   int client_id = 0, nclients = 1, iters = 20;
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--mode") && i + 1 < argc) mode = argv[++i];
@@ -123,6 +126,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--sweep-bytes") && i + 1 < argc) sweep_bytes = strtoull(argv[++i], NULL, 0);
     else if (!strcmp(argv[i], "--out") && i + 1 < argc) out_path = argv[++i];
     else if (!strcmp(argv[i], "--barrier-dir") && i + 1 < argc) barrier_dir = argv[++i];
+    else if (!strcmp(argv[i], "--start-barrier-dir") && i + 1 < argc) start_barrier_dir = argv[++i];
     else if (!strcmp(argv[i], "--client-id") && i + 1 < argc) client_id = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--nclients") && i + 1 < argc) nclients = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--iters") && i + 1 < argc) iters = atoi(argv[++i]);
@@ -149,6 +153,7 @@ int main(int argc, char** argv) {
   CUevent e0, e1;
   CK(cuEventCreate(&e0, CU_EVENT_DEFAULT));
   CK(cuEventCreate(&e1, CU_EVENT_DEFAULT));
+  barrier(start_barrier_dir, client_id, nclients, "start");
 
   if (!strcmp(mode, "storm")) {
     /* un-timed warm-up steps, barrier, then exactly K timed steps */

@@ -95,10 +95,12 @@ def run_arm(which, fracs, wargs, timeout=900, extra_env=None):
                     e.update(LD_PRELOAD=kb.LIB_PATH, GEMHOOK_POOL=os.path.join(tmp, "pool"), GEMHOOK_QUOTA_FILE=os.path.join(tmp, "quota.txt"),
                              GEMHOOK_STATS_FILE=os.path.join(tmp, "stats.%d.json"), GEMHOOK_TOKEN_TRACE=os.path.join(tmp, "trace.%d.jsonl"))
                     e.update({k: str(v) for k, v in (extra_env or {}).items()})
-                # no start barrier: a client that waits at a barrier sits on its token (up to a whole quota) while its peer
-                # cannot move -- idle-hold time that varies from run to run and is not what is being compared
+                # No barrier once tokens exist: a client that waits at a barrier sits on its token (up to a whole quota) while
+                # its peer cannot move -- idle-hold time that varies from run to run and is not what is being compared.  But
+                # one BEFORE the first call any hook intercepts: a peer that is still creating its context stalls the device
+                # for the client that already runs on a token (50-120 ms of ledger time without progress, in any stack).
                 procs.append(sp.Popen([kb.STORM_PATH, *map(str, wargs), "--client-id", str(i), "--nclients", str(n),
-                                       "--out", os.path.join(tmp, "out%d.json" % i)], env=e, stderr=sp.PIPE))
+                                       "--start-barrier-dir", tmp, "--out", os.path.join(tmp, "out%d.json" % i)], env=e, stderr=sp.PIPE))
             for p in procs:
                 _, err = p.communicate(timeout=timeout)
                 assert p.returncode == 0, err.decode()[-1500:]
