@@ -77,6 +77,33 @@ static void barrier(const char* dir, int id, int n, const char* tag) {
   }
 }
 
+/* --track-blocked: every launch is timed with rdtsc; a call that takes longer than 5 ms waited for a token (a launch costs
+ * ~2 us, draining 1024 noops ~2 ms).  What is left of the client's run time after those calls is the time it really had
+ * the GPU -- measured by the client itself, whatever hook is loaded. */
+static int track_blocked = 0;
+static double ticks_per_ns = 0;
+static unsigned long long blocked_thr = 0, blocked_ticks = 0;
+static void calibrate_tsc(void) { /* TSC ticks per ns, over 20 ms */
+  if (ticks_per_ns > 0) return;
+  double a = now_s();
+  unsigned long long c0 = __builtin_ia32_rdtsc();
+  while (now_s() - a < 0.02) {}
+  ticks_per_ns = (double)(__builtin_ia32_rdtsc() - c0) / ((now_s() - a) * 1e9);
+  blocked_thr = (unsigned long long)(ticks_per_ns * 5e6);
+}
+#define TRACKED(call)                                             \
+  do {                                                            \
+    if (track_blocked) {                                          \
+      unsigned long long c_ = __builtin_ia32_rdtsc();             \
+      CK(call);                                                   \
+      unsigned long long d_ = __builtin_ia32_rdtsc() - c_;        \
+      if (d_ > blocked_thr) blocked_ticks += d_;                  \
+    } else {                                                      \
+      CK(call);                                                   \
+    }                                                             \
+  } while (0)
+static double blocked_seconds(void) { return ticks_per_ns > 0 ? (double)blocked_ticks / ticks_per_ns / 1e9 : 0.0; }
+
 static CUfunction f_noop, f_spin, f_conv, f_spin_stamp;
 
 /* multi-threaded client: every thread launches on its own stream and synchronises now and then */
@@ -102,7 +129,6 @@ static void* mt_worker(void* p) {
 int main(int argc, char** argv) {
   const char* mode = "storm";
   long step_launches = 65536, sync_every = 1024, steps = 16, warmup = 3, rounds = 2000;
-  int track_blocked = 0; /* storm mode: time every driver call (rdtsc); calls longer than 5 ms are "blocked" (token waits) */
   double pace_ns = 0; /* storm mode: host-side delay added after every launch (how a slower launcher would look) */
   double spin_us = 5.0, sleep_mean_ms = 2.0;
   unsigned long long sweep_bytes = 40ULL << 30;
@@ -167,29 +193,11 @@ int main(int argc, char** argv) {
     }
     barrier(barrier_dir, client_id, nclients, "ready");
     double* step_s = (double*)calloc((size_t)steps + 1, sizeof(double));
-    unsigned long long pace_ticks = 0, blocked_thr = 0, blocked_ticks = 0;
-    double ticks_per_ns = 0;
-    if (pace_ns > 0 || track_blocked) { /* TSC ticks per ns, over 20 ms */
-      double a = now_s();
-      unsigned long long c0 = __builtin_ia32_rdtsc();
-      while (now_s() - a < 0.02) {}
-      ticks_per_ns = (double)(__builtin_ia32_rdtsc() - c0) / ((now_s() - a) * 1e9);
+    unsigned long long pace_ticks = 0;
+    if (pace_ns > 0 || track_blocked) {
+      calibrate_tsc();
       pace_ticks = (unsigned long long)(ticks_per_ns * pace_ns);
-      blocked_thr = (unsigned long long)(ticks_per_ns * 5e6);
     }
-    /* a hooked call that takes longer than 5 ms waited for a token (a launch costs ~2 us, draining 1024 noops ~2 ms):
-     * what is left of the client's run time after those calls is the time it really had the GPU */
-#define TRACKED(call)                                             \
-  do {                                                            \
-    if (track_blocked) {                                          \
-      unsigned long long c_ = __builtin_ia32_rdtsc();             \
-      CK(call);                                                   \
-      unsigned long long d_ = __builtin_ia32_rdtsc() - c_;        \
-      if (d_ > blocked_thr) blocked_ticks += d_;                  \
-    } else {                                                      \
-      CK(call);                                                   \
-    }                                                             \
-  } while (0)
     TRACKED(cuCtxSynchronize());
     double t0 = now_s();
     CK(cuEventRecord(e0, NULL));
@@ -206,7 +214,6 @@ int main(int argc, char** argv) {
       CK(cuCtxSynchronize());
       step_s[s] = now_s() - ts;
     }
-#undef TRACKED
     CK(cuEventRecord(e1, NULL));
     CK(cuEventSynchronize(e1));
     double t1 = now_s();
@@ -217,7 +224,7 @@ int main(int argc, char** argv) {
             "\"step_launches\": %ld, \"sync_every\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f, \"t0\": %.9f, "
             "\"t1\": %.9f, \"t_first\": %.9f, \"t_last\": %.9f, \"blocked_s\": %.9f, \"step_s\": [",
             client_id, steps * step_launches, steps, warmup, step_launches, sync_every, t1 - t0, ev_ms, t0, t1, t_first, t1,
-            ticks_per_ns > 0 ? (double)blocked_ticks / ticks_per_ns / 1e9 : 0.0);
+            blocked_seconds());
     for (long s = 0; s < steps; s++) fprintf(out, "%s%.9f", s ? ", " : "", step_s[s]);
     fprintf(out, "]}\n");
   } else if (!strcmp(mode, "bursty")) {
@@ -290,8 +297,9 @@ int main(int argc, char** argv) {
     const int N = 64;
     /* the very first intercepted call is a launch, so that every hook flavour asks for its first token at the same
      * point (the reference initialises -- and requests -- inside whichever hooked call comes first, e.g. cuMemAlloc) */
+    if (track_blocked) calibrate_tsc();
     double t_first = now_s();
-    CK(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
+    TRACKED(cuLaunchKernel(f_noop, 1, 1, 1, 32, 1, 1, 0, NULL, NULL, NULL));
     CK(cuCtxSynchronize());
     CUdeviceptr d_in, d_w1, d_a1, d_w2, d_a2;
     CK(cuMemAlloc(&d_in, (size_t)N * 1 * 784 * 4));
@@ -318,8 +326,8 @@ int main(int argc, char** argv) {
     CK(cuEventRecord(e0, NULL));
     for (int it = 0; it < iters; it++) {
       for (int k = 0; k < 50; k++) {
-        CK(cuLaunchKernel(f_conv, 32, N, 1, 28, 28, 1, 0, NULL, a1, NULL));
-        CK(cuLaunchKernel(f_conv, 64, N, 1, 28, 28, 1, 0, NULL, a2, NULL));
+        TRACKED(cuLaunchKernel(f_conv, 32, N, 1, 28, 28, 1, 0, NULL, a1, NULL));
+        TRACKED(cuLaunchKernel(f_conv, 64, N, 1, 28, 28, 1, 0, NULL, a2, NULL));
         launches += 2;
       }
       CK(dtoh(host, d_a2, 64 * 4));
@@ -330,7 +338,8 @@ int main(int argc, char** argv) {
     float ev_ms = 0;
     CK(cuEventElapsedTime(&ev_ms, e0, e1));
     fprintf(out, "{\"mode\": \"mnist\", \"client\": %d, \"iters\": %d, \"launches\": %ld, \"wall_s\": %.9f, \"event_ms\": %.6f, "
-            "\"t_first\": %.9f, \"t_last\": %.9f}\n", client_id, iters, launches, t1 - t0, ev_ms, t_first, t1);
+            "\"t_first\": %.9f, \"t_last\": %.9f, \"blocked_s\": %.9f}\n", client_id, iters, launches, t1 - t0, ev_ms, t_first, t1,
+            blocked_seconds());
   } else if (!strcmp(mode, "resolve")) {
     /* the three ways an application reaches the driver: direct symbol, dlsym(), cuGetProcAddress */
     typedef CUresult (*launch_t)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
