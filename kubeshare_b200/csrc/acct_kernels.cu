@@ -262,6 +262,33 @@ __device__ __forceinline__ void publish_page(unsigned nslots, u64* __restrict__ 
   }
 }
 
+// After every warp folded its bins into its accumulators: fold the warps (thread t handles (slot, field) t; ONE atomic per
+// (slot, field) per block), then the last block of the launch (threadfence + ticket) publishes.  Called by the whole block.
+__device__ __forceinline__ void block_epilogue(unsigned char* smem, unsigned nwarps, unsigned nslots, u64* __restrict__ dev_totals,
+                                               unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page,
+                                               const gemhook_mem_mirror& mm, u64* __restrict__ dev_mem) {
+  __syncthreads();
+  const u64* acc0 = reinterpret_cast<const u64*>(smem + (size_t)nwarps * (nslots + 1u) * COLS * 16u);
+  for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
+    u64 v = 0ull;
+    for (unsigned w = 0; w < nwarps; w++) v += acc0[(size_t)w * nslots * 3u + t];
+    if (v) atomicAdd(dev_totals + t, v);
+  }
+  __shared__ unsigned is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicAdd(ticket, 1u);
+    is_last = (prev == gridDim.x - 1u) ? 1u : 0u;
+    if (is_last) *ticket = 0u;  // self-reset for the next launch (stream-ordered)
+  }
+  __syncthreads();
+  if (is_last && page) {
+    __threadfence();
+    publish_page(nslots, dev_totals, page, mm, dev_mem);
+  }
+}
+
 extern "C" {
 
 // dev_totals: [nslots][3] u64 running totals + 1 u64 publish counter (device memory, persistent)
@@ -332,30 +359,103 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* 
     }
   }
   fold_bins(cells, acc, nslots, lane, false);
-  __syncthreads();
+  block_epilogue(smem, nwarps, nslots, dev_totals, ticket, page, mm, dev_mem);
+}
 
-  // fold warps: thread t handles (slot, field) t; ONE atomic per (slot, field) per block
-  const u64* acc0 = reinterpret_cast<const u64*>(smem + (size_t)nwarps * (nslots + 1u) * COLS * 16u);
-  for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
-    u64 v = 0ull;
-    for (unsigned w = 0; w < nwarps; w++) v += acc0[(size_t)w * nslots * 3u + t];
-    if (v) atomicAdd(dev_totals + t, v);
-  }
+// ---- many client slots: the same accumulation fed by TMA bulk copies -------------------------------------------------
+// Bins of 64 slots take 34.8 KB per warp, so only a handful of warps fit into an SM, and with register-staged loads
+// (UNROLL x 16 B per lane, two tiles) a handful of warps cannot keep the ~36 KB per SM in flight that HBM needs: measured
+// 0.55 / 0.65 / 0.74 of the roofline with 4 / 5 / 6 warps -- proportional to the warp count, i.e. bound by bytes in flight,
+// not by the bin updates.  Here every warp owns a ring of `stages` 4 KB buffers in shared memory that lane 0 keeps filled
+// with cp.async.bulk (SASS UBLKCP, completion counted on an mbarrier per buffer): the bytes in flight are set by the ring,
+// not by the register file, and four warps are enough for the arithmetic (one 32-record row per ~90 cycles per warp).
+// dynamic shared memory: bins + accumulators of the warps as above, then (16-byte aligned) warps x stages x 4096 bytes of
+// staging and warps x stages mbarriers.
+#define STG_TILE_BYTES (32u * GEMHOOK_UNROLL * 16u)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_fill(unsigned dst, const uint4* src, unsigned bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(STG_TILE_BYTES) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(STG_TILE_BYTES), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void stage_wait(unsigned bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
 
-  // last block of the launch (threadfence + ticket) publishes
-  __shared__ unsigned is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned prev = atomicAdd(ticket, 1u);
-    is_last = (prev == gridDim.x - 1u) ? 1u : 0u;
-    if (is_last) *ticket = 0u;  // self-reset for the next launch (stream-ordered)
+__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 1)
+gemhook_acct_reduce_staged(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals,
+                           unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm,
+                           u64* __restrict__ dev_mem, unsigned flush_every, unsigned stages) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const unsigned nwarps = blockDim.x >> 5;
+  uint4* cells = reinterpret_cast<uint4*>(smem) + (size_t)warp * (nslots + 1u) * COLS;
+  u64* acc = reinterpret_cast<u64*>(smem + (size_t)nwarps * (nslots + 1u) * COLS * 16u) + (size_t)warp * nslots * 3u;
+  const unsigned bins_bytes = nwarps * ((nslots + 1u) * COLS * 16u + nslots * 24u);
+  unsigned char* stg_all = smem + ((bins_bytes + 15u) & ~15u);  // (cp.async.bulk: 16-byte aligned destination)
+  const unsigned stg = smem_u32(stg_all) + warp * stages * STG_TILE_BYTES;
+  const unsigned bars = smem_u32(stg_all) + nwarps * stages * STG_TILE_BYTES + warp * stages * 8u;
+
+  zero_bins(cells, nslots, lane);
+  for (unsigned t = lane; t < nslots * 3u; t += 32u) acc[t] = 0ull;
+  if (lane == 0) {
+    for (unsigned s = 0; s < stages; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + s * 8u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  if (is_last && page) {
-    __threadfence();
-    publish_page(nslots, dev_totals, page, mm, dev_mem);
+  __syncwarp();
+
+  const u64 tile = 32ull * GEMHOOK_UNROLL;  // records per stage
+  const u64 full = n / tile;                // whole tiles: bulk copies; the ragged rest goes through plain loads below
+  const u64 gw = (u64)blockIdx.x * nwarps + warp, GW = (u64)gridDim.x * nwarps;
+  // this warp's k-th tile is tile gw + k * GW; its buffer is k % stages, used for the (k / stages)-th time
+  if (lane == 0) {
+    for (unsigned k = 0; k < stages; k++) {
+      const u64 t = gw + (u64)k * GW;
+      if (t < full) stage_fill(stg + k * STG_TILE_BYTES, rec + t * tile, bars + k * 8u);
+    }
   }
+  unsigned since_flush = 0, s = 0, parity = 0;
+  for (u64 t = gw; t < full; t += GW) {
+    stage_wait(bars + s * 8u, parity);
+    uint4 r[GEMHOOK_UNROLL];
+    const uint4* buf = reinterpret_cast<const uint4*>(stg_all + (size_t)(warp * stages + s) * STG_TILE_BYTES);
+#pragma unroll
+    for (int u = 0; u < GEMHOOK_UNROLL; u++) r[u] = lds128(buf + (unsigned)u * 32u + lane);
+    bin_add_tile<GEMHOOK_UNROLL>(cells, nslots, lane, r);
+    // every lane has consumed its rows (the bin updates depend on them): the buffer may be overwritten
+    __syncwarp();
+    const u64 nt = t + (u64)stages * GW;
+    if (lane == 0 && nt < full) stage_fill(stg + s * STG_TILE_BYTES, rec + nt * tile, bars + s * 8u);
+    if (++s == stages) {
+      s = 0;
+      parity ^= 1u;
+    }
+    if (++since_flush >= flush_every) {
+      fold_bins(cells, acc, nslots, lane, true);
+      since_flush = 0;
+    }
+  }
+  if (gw == full % GW) {  // ragged tail of the ring (< one tile): the warp whose turn it would be
+#pragma unroll 1
+    for (int u = 0; u < GEMHOOK_UNROLL; u++) {
+      const u64 i = full * tile + (unsigned)u * 32u + lane;
+      const uint4 r = i < n ? ld_stream_16(rec + i) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+      bin_add_tile<1>(cells, nslots, lane, &r);
+    }
+  }
+  fold_bins(cells, acc, nslots, lane, false);
+  block_epilogue(smem, nwarps, nslots, dev_totals, ticket, page, mm, dev_mem);
 }
 
 // The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight

@@ -40,6 +40,7 @@ struct mem_mirror {  // mirrors gemhook_mem_mirror (kernel parameter, by value)
 #define GEMHOOK_UNROLL 8
 #endif
 const unsigned TILE_RECORDS = 32u * GEMHOOK_UNROLL;  // records per warp iteration (32 lanes x GEMHOOK_UNROLL)
+const unsigned STAGED_MIN_SLOTS = 16;                // above this many client slots the TMA-staged kernel runs (measured crossover)
 const size_t SMALL_N = 512;                          // up to here one warp does everything (gemhook_acct_reduce_small);
                                                      // measured: 10.5 vs 12.7 us at 2-64 records, break-even near 1024
 // shared memory per warp: (nslots + 1) rows of 32 16-byte cells (the extra row swallows out-of-range slots) + the
@@ -69,7 +70,7 @@ const char* cu_err(CUresult r) {
 struct gemhook_acct {
   CUcontext ctx = nullptr;
   CUmodule mod = nullptr;
-  CUfunction f_reduce = nullptr, f_small = nullptr, f_clear = nullptr, f_peek = nullptr;
+  CUfunction f_reduce = nullptr, f_small = nullptr, f_clear = nullptr, f_peek = nullptr, f_staged = nullptr;
   CUstream stream = nullptr;
   CUevent ev0 = nullptr, ev1 = nullptr;
   CUdeviceptr d_ring = 0, d_totals = 0, d_ticket = 0, d_page = 0, d_mem = 0;
@@ -77,6 +78,7 @@ struct gemhook_acct {
   size_t ring_cap = 0;
   uint32_t nslots = 0;
   unsigned warps = 8, smem_bytes = 0, small_smem = 0, max_blocks = 0, flush_every = 8000;
+  unsigned stages = 0;  // > 0: the TMA-staged kernel (many client slots) with this many 4 KB buffers per warp
   int sm_count = 0;
   mem_mirror mm = {0, 0, 0};
   bool small_enabled = true;
@@ -131,7 +133,41 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
     if (f >= 1u && f <= 8000u) a->flush_every = f;
   }
   if (const char* e = getenv("GEMHOOK_ACCT_SMALL")) a->small_enabled = atoi(e) != 0;
+  // Many client slots: the bins leave room for only a few warps, and a few warps with register-staged loads cannot keep
+  // HBM busy.  gemhook_acct_reduce_staged feeds the same accumulation from per-warp rings of 4 KB buffers filled by
+  // cp.async.bulk, so the bytes in flight are set by the ring: pick the largest warp count (one block per SM) that still
+  // leaves every warp >= 2 buffers and the SM >= 48 KB in flight (the HBM latency x bandwidth product is ~36 KB per SM).
+  const unsigned SMEM_MAX = 227u * 1024u, STG = TILE_RECORDS * 16u + 8u;
+  bool staged = nslots > STAGED_MIN_SLOTS;
+  if (const char* e = getenv("GEMHOOK_ACCT_STAGED")) staged = atoi(e) != 0;
+  if (staged) {
+    unsigned best_w = 0, best_s = 0;
+    for (unsigned w = 8; w >= 1 && !best_w; w--) {
+      if (w * per_warp + 16u + w * 2u * STG > SMEM_MAX) continue;
+      unsigned s_ = (SMEM_MAX - w * per_warp - 16u) / (w * STG);
+      if (s_ > 8u) s_ = 8u;
+      if (w * s_ >= 12u || w == 1u) best_w = w, best_s = s_;
+    }
+    if (const char* e = getenv("GEMHOOK_ACCT_WARPS")) {
+      unsigned w = (unsigned)atoi(e);
+      if (w >= 1u && w <= 8u && w * per_warp + 16u + w * 2u * STG <= SMEM_MAX) {
+        best_w = w;
+        best_s = (SMEM_MAX - w * per_warp - 16u) / (w * STG);
+        if (best_s > 8u) best_s = 8u;
+      }
+    }
+    if (const char* e = getenv("GEMHOOK_ACCT_STAGES")) {
+      unsigned s_ = (unsigned)atoi(e);
+      if (s_ >= 1u && best_w && best_w * per_warp + 16u + best_w * s_ * STG <= SMEM_MAX) best_s = s_;
+    }
+    if (best_w && best_s) {
+      a->warps = best_w;
+      a->stages = best_s;
+      blocks_per_sm = 1;
+    }
+  }
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, "gemhook_acct_reduce"));
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_staged, a->mod, "gemhook_acct_reduce_staged"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_small, a->mod, "gemhook_acct_reduce_small"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_clear, a->mod, "gemhook_acct_clear"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_peek, a->mod, "gemhook_peek_pool"));
@@ -141,12 +177,13 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
 
   a->nslots = nslots;
   a->smem_bytes = a->warps * per_warp;
+  if (a->stages) a->smem_bytes = ((a->smem_bytes + 15u) & ~15u) + a->warps * a->stages * STG;
   a->small_smem = (nslots + 1u) * GEMHOOK_COLS * 16u;
+  CUfunction f_big = a->stages ? a->f_staged : a->f_reduce;
   if (a->smem_bytes > 48u * 1024u)
-    CU_TRY(GH_CALL(cuFuncSetAttribute, a->f_reduce, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)a->smem_bytes));
+    CU_TRY(GH_CALL(cuFuncSetAttribute, f_big, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)a->smem_bytes));
   int per_sm = 0;
-  CU_TRY(GH_CALL(cuOccupancyMaxActiveBlocksPerMultiprocessor, &per_sm, a->f_reduce, (int)(a->warps * 32u),
-                 (size_t)a->smem_bytes));
+  CU_TRY(GH_CALL(cuOccupancyMaxActiveBlocksPerMultiprocessor, &per_sm, f_big, (int)(a->warps * 32u), (size_t)a->smem_bytes));
   if (per_sm < 1) per_sm = 1;
   if ((unsigned)per_sm > blocks_per_sm) per_sm = (int)blocks_per_sm;
   a->max_blocks = (unsigned)(per_sm * a->sm_count);  // one full wave: a multiple of the SM count
@@ -166,8 +203,8 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   a->page = (totals_page*)hp;
   CU_TRY(GH_CALL(cuMemHostGetDevicePointer_v2, &a->d_page, hp, 0));
   CU_TRY(GH_CALL(cuStreamSynchronize, a->stream));
-  GH_INFO("acct: %d SMs, nslots %u, %u warps/block, %u B smem, wave %u blocks (%d per SM)", a->sm_count, nslots, a->warps,
-          a->smem_bytes, a->max_blocks, per_sm);
+  GH_INFO("acct: %d SMs, nslots %u, %u warps/block, %u B smem, wave %u blocks (%d per SM), %u TMA stages per warp", a->sm_count,
+          nslots, a->warps, a->smem_bytes, a->max_blocks, per_sm, a->stages);
   return 0;
 }
 
@@ -213,9 +250,10 @@ static int launch_reduce(gemhook_acct* a, CUdeviceptr d_rec, size_t n) {
     CU_TRY(GH_CALL(cuLaunchKernel, a->f_small, 1, 1, 1, 32, 1, 1, a->small_smem, a->stream, args, nullptr));
   } else {
     unsigned long long nn = n;
-    void* args[] = {&d_rec, &nn, &ns, &a->d_totals, &a->d_ticket, &a->d_page, &a->mm, &a->d_mem, &a->flush_every};
-    unsigned grid = gemhook_acct_grid_for(a, n);
-    CU_TRY(GH_CALL(cuLaunchKernel, a->f_reduce, grid, 1, 1, a->warps * 32u, 1, 1, a->smem_bytes, a->stream, args, nullptr));
+    void* args[] = {&d_rec, &nn, &ns, &a->d_totals, &a->d_ticket, &a->d_page, &a->mm, &a->d_mem, &a->flush_every, &a->stages};
+    unsigned grid = gemhook_acct_grid_for(a, n);  // (the staged kernel takes one more parameter: the ring depth)
+    CU_TRY(GH_CALL(cuLaunchKernel, a->stages ? a->f_staged : a->f_reduce, grid, 1, 1, a->warps * 32u, 1, 1, a->smem_bytes, a->stream,
+                   args, nullptr));
   }
   a->kernel_launches.fetch_add(1, std::memory_order_relaxed);
   a->reduce_launches.fetch_add(1, std::memory_order_relaxed);

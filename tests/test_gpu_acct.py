@@ -136,6 +136,29 @@ def test_fast_path_boundary_and_equivalence(torch_cuda, OL, nslots, n, monkeypat
             a.close()
 
 
+@pytest.mark.parametrize("nslots,warps,stages", [(3, 8, 2), (17, 8, 3), (33, 6, 4), (64, 4, 5), (64, 5, 2), (64, 1, 8)])
+@pytest.mark.parametrize("n", [513, 767, 768, 769, 4096, 70_001, (1 << 21) + 255])
+def test_tma_staged_kernel_matches_oracle_and_the_register_staged_one(torch_cuda, OL, nslots, warps, stages, n, monkeypatch):
+    """gemhook_acct_reduce_staged (above 16 client slots by default): the same bins fed from per-warp rings of 4 KB
+    buffers filled with cp.async.bulk.  Forced on for small slot counts too, with ring depths 2..8, sizes that are not a
+    multiple of the 256-record tile, fewer tiles than warps, and the in-kernel flush every 2 tiles -- bit-exact against the
+    oracle, hence equal to the register-staged kernel."""
+    monkeypatch.setenv("GEMHOOK_ACCT_SMALL", "0")
+    monkeypatch.setenv("GEMHOOK_ACCT_FLUSH_EVERY", "2")
+    r = make_records(n, nslots, seed=n + 31 * nslots + stages, big=True)
+    want = oracle(OL, r, nslots)
+    for staged in ("1", "0"):
+        monkeypatch.setenv("GEMHOOK_ACCT_STAGED", staged)
+        monkeypatch.setenv("GEMHOOK_ACCT_WARPS", str(warps))
+        monkeypatch.setenv("GEMHOOK_ACCT_STAGES", str(stages))
+        a = kb.Acct(nslots, ring_capacity=1 << 22)
+        try:
+            assert (a.reduce_host(r) == want).all(), staged
+            assert (a.reduce_host(r) == want + want).all(), staged
+        finally:
+            a.close()
+
+
 @pytest.mark.parametrize("every", [1, 3])
 def test_in_kernel_bin_flush_is_exact(torch_cuda, OL, every, monkeypatch):
     """The packed (count << 48 | launches) half of a bin cell holds < 2^16 records per column; the kernel folds its bins
