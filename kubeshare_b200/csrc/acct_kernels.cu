@@ -152,9 +152,9 @@ __device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, uns
 #pragma unroll
   for (int j = 0; j < G; j++) sts128(cells + sl[j] * COLS + col, v[j]);
 }
-template <int U>
+template <int U, int ILP = GEMHOOK_ILP>
 __device__ __forceinline__ void bin_add_tile(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
-  constexpr int G = (GEMHOOK_ILP <= U && U % GEMHOOK_ILP == 0) ? GEMHOOK_ILP : 1;
+  constexpr int G = (ILP <= U && U % ILP == 0) ? ILP : 1;
   const unsigned col = lane & (COLS - 1u);
 #pragma unroll
   for (unsigned ph = 0; ph < 32u / COLS; ph++) {  // lanes sharing a column take turns
@@ -392,10 +392,13 @@ __device__ __forceinline__ void stage_wait(unsigned bar, unsigned parity) {
   } while (!done);
 }
 
-__global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 1)
-gemhook_acct_reduce_staged(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals,
-                           unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm,
-                           u64* __restrict__ dev_mem, unsigned flush_every, unsigned stages) {
+}  // extern "C"
+
+template <int ILP>
+__device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals,
+                                                   unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page,
+                                                   const gemhook_mem_mirror& mm, u64* __restrict__ dev_mem, unsigned flush_every,
+                                                   unsigned stages) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
@@ -432,7 +435,7 @@ gemhook_acct_reduce_staged(const uint4* __restrict__ rec, u64 n, unsigned nslots
     const uint4* buf = reinterpret_cast<const uint4*>(stg_all + (size_t)(warp * stages + s) * STG_TILE_BYTES);
 #pragma unroll
     for (int u = 0; u < GEMHOOK_UNROLL; u++) r[u] = lds128(buf + (unsigned)u * 32u + lane);
-    bin_add_tile<GEMHOOK_UNROLL>(cells, nslots, lane, r);
+    bin_add_tile<GEMHOOK_UNROLL, ILP>(cells, nslots, lane, r);
     // every lane has consumed its rows (the bin updates depend on them): the buffer may be overwritten
     __syncwarp();
     const u64 nt = t + (u64)stages * GW;
@@ -457,6 +460,22 @@ gemhook_acct_reduce_staged(const uint4* __restrict__ rec, u64 n, unsigned nslots
   fold_bins(cells, acc, nslots, lane, false);
   block_epilogue(smem, nwarps, nslots, dev_totals, ticket, page, mm, dev_mem);
 }
+
+extern "C" {
+
+// With one warp per scheduler (four warps per SM at 64 slots) instruction latency is exposed: the group size of the bin
+// update (independent read-modify-write chains per lane) is what the per-warp rate depends on.  Variants by group size;
+// the host picks one (gh_acct.cpp).
+#define STAGED_KERNEL(NAME, ILP)                                                                                            \
+  __global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 1)                                                    \
+  NAME(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals, unsigned* __restrict__ ticket, \
+       gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm, u64* __restrict__ dev_mem, unsigned flush_every,     \
+       unsigned stages) {                                                                                                  \
+    reduce_staged_body<ILP>(rec, n, nslots, dev_totals, ticket, page, mm, dev_mem, flush_every, stages);                   \
+  }
+STAGED_KERNEL(gemhook_acct_reduce_staged, 2)
+STAGED_KERNEL(gemhook_acct_reduce_staged_g4, 4)
+STAGED_KERNEL(gemhook_acct_reduce_staged_g8, 8)
 
 // The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight
 // warps, no shuffle trees, no ticket; the running totals come back from the atomics themselves, so nothing is re-read.

@@ -167,7 +167,14 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
     }
   }
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, "gemhook_acct_reduce"));
-  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_staged, a->mod, "gemhook_acct_reduce_staged"));
+  {
+    const char* name = "gemhook_acct_reduce_staged";
+    if (const char* e = getenv("GEMHOOK_ACCT_STAGED_ILP")) {  // sweeps: group size of the bin update (2, 4, 8)
+      if (atoi(e) == 4) name = "gemhook_acct_reduce_staged_g4";
+      if (atoi(e) == 8) name = "gemhook_acct_reduce_staged_g8";
+    }
+    CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_staged, a->mod, name));
+  }
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_small, a->mod, "gemhook_acct_reduce_small"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_clear, a->mod, "gemhook_acct_clear"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_peek, a->mod, "gemhook_peek_pool"));
