@@ -152,6 +152,33 @@ __device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, uns
 #pragma unroll
   for (int j = 0; j < G; j++) sts128(cells + sl[j] * COLS + col, v[j]);
 }
+// U records of one lane, software-pipelined: the cell of record u+1 is loaded BEFORE the cell of record u is stored, so the
+// load latency of one record overlaps the adds of the previous one; if the two records name the same cell the loaded value
+// is stale and the value just computed is forwarded instead (one compare + four selects per record, no merging pass).
+template <int U>
+__device__ __forceinline__ void bin_add_tile_fwd(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
+  unsigned off[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) off[u] = min(r[u].x, nslots) * COLS + lane;
+  uint4 cur = lds128(cells + off[0]);
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (u + 1 < U) nxt = lds128(cells + off[u + 1]);
+    const u64 a = (((u64)cur.y << 32) | cur.x) + (((u64)r[u].w << 32) | r[u].z);
+    const u64 b = (((u64)cur.w << 32) | cur.z) + (PK_ONE | (u64)r[u].y);
+    const uint4 nv = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
+    sts128(cells + off[u], nv);
+    if (u + 1 < U) {
+      const bool same = off[u + 1] == off[u];
+      cur.x = same ? nv.x : nxt.x;
+      cur.y = same ? nv.y : nxt.y;
+      cur.z = same ? nv.z : nxt.z;
+      cur.w = same ? nv.w : nxt.w;
+    }
+  }
+}
+
 template <int U, int ILP = GEMHOOK_ILP>
 __device__ __forceinline__ void bin_add_tile(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
   constexpr int G = (ILP <= U && U % ILP == 0) ? ILP : 1;
@@ -435,7 +462,8 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
     const uint4* buf = reinterpret_cast<const uint4*>(stg_all + (size_t)(warp * stages + s) * STG_TILE_BYTES);
 #pragma unroll
     for (int u = 0; u < GEMHOOK_UNROLL; u++) r[u] = lds128(buf + (unsigned)u * 32u + lane);
-    bin_add_tile<GEMHOOK_UNROLL, ILP>(cells, nslots, lane, r);
+    if (ILP == 0) bin_add_tile_fwd<GEMHOOK_UNROLL>(cells, nslots, lane, r);
+    else bin_add_tile<GEMHOOK_UNROLL, (ILP > 0 ? ILP : 1)>(cells, nslots, lane, r);
     // every lane has consumed its rows (the bin updates depend on them): the buffer may be overwritten
     __syncwarp();
     const u64 nt = t + (u64)stages * GW;
@@ -476,6 +504,8 @@ extern "C" {
 STAGED_KERNEL(gemhook_acct_reduce_staged, 2)
 STAGED_KERNEL(gemhook_acct_reduce_staged_g4, 4)
 STAGED_KERNEL(gemhook_acct_reduce_staged_g8, 8)
+STAGED_KERNEL(gemhook_acct_reduce_staged_g1, 1)
+STAGED_KERNEL(gemhook_acct_reduce_staged_fwd, 0)
 
 // The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight
 // warps, no shuffle trees, no ticket; the running totals come back from the atomics themselves, so nothing is re-read.

@@ -172,6 +172,8 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
     if (const char* e = getenv("GEMHOOK_ACCT_STAGED_ILP")) {  // sweeps: group size of the bin update (2, 4, 8)
       if (atoi(e) == 4) name = "gemhook_acct_reduce_staged_g4";
       if (atoi(e) == 8) name = "gemhook_acct_reduce_staged_g8";
+      if (atoi(e) == 1) name = "gemhook_acct_reduce_staged_g1";
+      if (atoi(e) == 0) name = "gemhook_acct_reduce_staged_fwd";
     }
     CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_staged, a->mod, name));
   }
