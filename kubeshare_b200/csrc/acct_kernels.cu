@@ -103,8 +103,9 @@ __device__ __forceinline__ void sts128(uint4* p, const uint4& v) {
 
 // one record into the warp's bins: cell (slot, lane) = {ns, count << 48 | launches}.  Branch-free: a slot outside
 // [0, nslots) lands in the trash row `nslots`, which is zeroed with the others and never folded.
+template <unsigned C = COLS>
 __device__ __forceinline__ void bin_add(uint4* cells, unsigned nslots, unsigned col, const uint4& r) {
-  uint4* c = cells + min(r.x, nslots) * COLS + col;
+  uint4* c = cells + min(r.x, nslots) * C + col;
   uint4 v = lds128(c);
   u64 ns = (((u64)v.y << 32) | v.x) + (((u64)r.w << 32) | r.z);
   u64 pk = (((u64)v.w << 32) | v.z) + (PK_ONE | (u64)r.y);
@@ -119,7 +120,7 @@ __device__ __forceinline__ void bin_add(uint4* cells, unsigned nslots, unsigned 
 #ifndef GEMHOOK_ILP
 #define GEMHOOK_ILP 2 /* measured (profiles/r02_acct_reduce_variants.jsonl): 1 -> 0.74, 2 -> 0.79, 4 -> 0.79 of the roofline at 64 slots */
 #endif
-template <int G>
+template <int G, unsigned C = COLS>
 __device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, unsigned col, const uint4* r) {
   unsigned sl[G];
   u64 ns[G], pk[G];
@@ -141,7 +142,7 @@ __device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, uns
   }
   uint4 v[G];
 #pragma unroll
-  for (int j = 0; j < G; j++) v[j] = lds128(cells + sl[j] * COLS + col);
+  for (int j = 0; j < G; j++) v[j] = lds128(cells + sl[j] * C + col);
 #pragma unroll
   for (int j = 0; j < G; j++) {
     u64 a = (((u64)v[j].y << 32) | v[j].x) + ns[j];
@@ -150,49 +151,55 @@ __device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, uns
   }
   // two redirected records of one group share the trash cell: whichever store lands last wins, nobody reads it
 #pragma unroll
-  for (int j = 0; j < G; j++) sts128(cells + sl[j] * COLS + col, v[j]);
+  for (int j = 0; j < G; j++) sts128(cells + sl[j] * C + col, v[j]);
 }
 // U records of one lane, software-pipelined: the cell of record u+1 is loaded BEFORE the cell of record u is stored, so the
 // load latency of one record overlaps the adds of the previous one; if the two records name the same cell the loaded value
 // is stale and the value just computed is forwarded instead (one compare + four selects per record, no merging pass).
-template <int U>
+template <int U, unsigned C = COLS>
 __device__ __forceinline__ void bin_add_tile_fwd(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
   unsigned off[U];
 #pragma unroll
-  for (int u = 0; u < U; u++) off[u] = min(r[u].x, nslots) * COLS + lane;
-  uint4 cur = lds128(cells + off[0]);
+  for (int u = 0; u < U; u++) off[u] = min(r[u].x, nslots) * C + (lane & (C - 1u));
 #pragma unroll
-  for (int u = 0; u < U; u++) {
-    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-    if (u + 1 < U) nxt = lds128(cells + off[u + 1]);
-    const u64 a = (((u64)cur.y << 32) | cur.x) + (((u64)r[u].w << 32) | r[u].z);
-    const u64 b = (((u64)cur.w << 32) | cur.z) + (PK_ONE | (u64)r[u].y);
-    const uint4 nv = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
-    sts128(cells + off[u], nv);
-    if (u + 1 < U) {
-      const bool same = off[u + 1] == off[u];
-      cur.x = same ? nv.x : nxt.x;
-      cur.y = same ? nv.y : nxt.y;
-      cur.z = same ? nv.z : nxt.z;
-      cur.w = same ? nv.w : nxt.w;
+  for (unsigned ph = 0; ph < 32u / C; ph++) {  // lanes sharing a column take turns
+    if (C == 32u || (lane / C) == ph) {
+      uint4 cur = lds128(cells + off[0]);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+        if (u + 1 < U) nxt = lds128(cells + off[u + 1]);
+        const u64 a = (((u64)cur.y << 32) | cur.x) + (((u64)r[u].w << 32) | r[u].z);
+        const u64 b = (((u64)cur.w << 32) | cur.z) + (PK_ONE | (u64)r[u].y);
+        const uint4 nv = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
+        sts128(cells + off[u], nv);
+        if (u + 1 < U) {
+          const bool same = off[u + 1] == off[u];
+          cur.x = same ? nv.x : nxt.x;
+          cur.y = same ? nv.y : nxt.y;
+          cur.z = same ? nv.z : nxt.z;
+          cur.w = same ? nv.w : nxt.w;
+        }
+      }
     }
+    if (C != 32u) __syncwarp();
   }
 }
 
-template <int U, int ILP = GEMHOOK_ILP>
+template <int U, int ILP = GEMHOOK_ILP, unsigned C = COLS>
 __device__ __forceinline__ void bin_add_tile(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
   constexpr int G = (ILP <= U && U % ILP == 0) ? ILP : 1;
-  const unsigned col = lane & (COLS - 1u);
+  const unsigned col = lane & (C - 1u);
 #pragma unroll
-  for (unsigned ph = 0; ph < 32u / COLS; ph++) {  // lanes sharing a column take turns
-    if (COLS == 32u || (lane / COLS) == ph) {
+  for (unsigned ph = 0; ph < 32u / C; ph++) {  // lanes sharing a column take turns
+    if (C == 32u || (lane / C) == ph) {
 #pragma unroll
       for (int u = 0; u < U; u += G) {
-        if (G == 1) bin_add(cells, nslots, col, r[u]);
-        else bin_add_group<G>(cells, nslots, col, r + u);
+        if (G == 1) bin_add<C>(cells, nslots, col, r[u]);
+        else bin_add_group<G, C>(cells, nslots, col, r + u);
       }
     }
-    if (COLS != 32u) __syncwarp();
+    if (C != 32u) __syncwarp();
   }
 }
 
@@ -209,24 +216,27 @@ __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
   for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
   return v;
 }
+template <unsigned C = COLS>
 __device__ __forceinline__ void warp_tree_slot(const uint4* cells, unsigned s, unsigned lane, u64& ns, u64& la, u64& rc) {
-  const bool own = lane < COLS;
-  uint4 v = own ? cells[s * COLS + lane] : make_uint4(0u, 0u, 0u, 0u);
+  const bool own = lane < C;
+  uint4 v = own ? cells[s * C + lane] : make_uint4(0u, 0u, 0u, 0u);
   u64 pk = ((u64)v.w << 32) | v.z;
   ns = warp_sum_u64(((u64)v.y << 32) | v.x);
   la = warp_sum_u64(pk & PK_MASK);
   rc = warp_sum_u64(pk >> 48);
 }
 
+template <unsigned C = COLS>
 __device__ __forceinline__ void zero_bins(uint4* cells, unsigned nslots, unsigned lane) {
-  for (unsigned t = lane; t < (nslots + 1u) * COLS; t += 32u) cells[t] = make_uint4(0u, 0u, 0u, 0u);
+  for (unsigned t = lane; t < (nslots + 1u) * C; t += 32u) cells[t] = make_uint4(0u, 0u, 0u, 0u);
 }
+template <unsigned C = COLS>
 __device__ __forceinline__ void fold_bins(uint4* cells, u64* acc, unsigned nslots, unsigned lane, bool rezero) {
   __syncwarp();
   if (nslots <= GEMHOOK_SHFL_SLOTS) {
     for (unsigned s = 0; s < nslots; s++) {
       u64 ns, la, rc;
-      warp_tree_slot(cells, s, lane, ns, la, rc);
+      warp_tree_slot<C>(cells, s, lane, ns, la, rc);
       if (lane == 0) {
         acc[s * 3u + 0u] += ns;
         acc[s * 3u + 1u] += la;
@@ -237,8 +247,8 @@ __device__ __forceinline__ void fold_bins(uint4* cells, u64* acc, unsigned nslot
   for (unsigned s = lane; s < nslots; s += 32u) {
     u64 ns = 0ull, la = 0ull, rc = 0ull;
 #pragma unroll 8
-    for (unsigned c = 0; c < COLS; c++) {
-      uint4 v = cells[s * COLS + ((c + lane) & (COLS - 1u))];
+    for (unsigned c = 0; c < C; c++) {
+      uint4 v = cells[s * C + ((c + lane) & (C - 1u))];
       u64 pk = ((u64)v.w << 32) | v.z;
       ns += ((u64)v.y << 32) | v.x;
       la += pk & PK_MASK;
@@ -250,7 +260,7 @@ __device__ __forceinline__ void fold_bins(uint4* cells, u64* acc, unsigned nslot
   }
   __syncwarp();
   if (rezero) {
-    zero_bins(cells, nslots, lane);
+    zero_bins<C>(cells, nslots, lane);
     __syncwarp();
   }
 }
@@ -291,11 +301,12 @@ __device__ __forceinline__ void publish_page(unsigned nslots, u64* __restrict__ 
 
 // After every warp folded its bins into its accumulators: fold the warps (thread t handles (slot, field) t; ONE atomic per
 // (slot, field) per block), then the last block of the launch (threadfence + ticket) publishes.  Called by the whole block.
+template <unsigned C = COLS>
 __device__ __forceinline__ void block_epilogue(unsigned char* smem, unsigned nwarps, unsigned nslots, u64* __restrict__ dev_totals,
                                                unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page,
                                                const gemhook_mem_mirror& mm, u64* __restrict__ dev_mem) {
   __syncthreads();
-  const u64* acc0 = reinterpret_cast<const u64*>(smem + (size_t)nwarps * (nslots + 1u) * COLS * 16u);
+  const u64* acc0 = reinterpret_cast<const u64*>(smem + (size_t)nwarps * (nslots + 1u) * C * 16u);
   for (unsigned t = threadIdx.x; t < nslots * 3u; t += blockDim.x) {
     u64 v = 0ull;
     for (unsigned w = 0; w < nwarps; w++) v += acc0[(size_t)w * nslots * 3u + t];
@@ -421,7 +432,7 @@ __device__ __forceinline__ void stage_wait(unsigned bar, unsigned parity) {
 
 }  // extern "C"
 
-template <int ILP>
+template <int ILP, unsigned C>
 __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals,
                                                    unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page,
                                                    const gemhook_mem_mirror& mm, u64* __restrict__ dev_mem, unsigned flush_every,
@@ -430,14 +441,14 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const unsigned nwarps = blockDim.x >> 5;
-  uint4* cells = reinterpret_cast<uint4*>(smem) + (size_t)warp * (nslots + 1u) * COLS;
-  u64* acc = reinterpret_cast<u64*>(smem + (size_t)nwarps * (nslots + 1u) * COLS * 16u) + (size_t)warp * nslots * 3u;
-  const unsigned bins_bytes = nwarps * ((nslots + 1u) * COLS * 16u + nslots * 24u);
+  uint4* cells = reinterpret_cast<uint4*>(smem) + (size_t)warp * (nslots + 1u) * C;
+  u64* acc = reinterpret_cast<u64*>(smem + (size_t)nwarps * (nslots + 1u) * C * 16u) + (size_t)warp * nslots * 3u;
+  const unsigned bins_bytes = nwarps * ((nslots + 1u) * C * 16u + nslots * 24u);
   unsigned char* stg_all = smem + ((bins_bytes + 15u) & ~15u);  // (cp.async.bulk: 16-byte aligned destination)
   const unsigned stg = smem_u32(stg_all) + warp * stages * STG_TILE_BYTES;
   const unsigned bars = smem_u32(stg_all) + nwarps * stages * STG_TILE_BYTES + warp * stages * 8u;
 
-  zero_bins(cells, nslots, lane);
+  zero_bins<C>(cells, nslots, lane);
   for (unsigned t = lane; t < nslots * 3u; t += 32u) acc[t] = 0ull;
   if (lane == 0) {
     for (unsigned s = 0; s < stages; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + s * 8u) : "memory");
@@ -462,8 +473,8 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
     const uint4* buf = reinterpret_cast<const uint4*>(stg_all + (size_t)(warp * stages + s) * STG_TILE_BYTES);
 #pragma unroll
     for (int u = 0; u < GEMHOOK_UNROLL; u++) r[u] = lds128(buf + (unsigned)u * 32u + lane);
-    if (ILP == 0) bin_add_tile_fwd<GEMHOOK_UNROLL>(cells, nslots, lane, r);
-    else bin_add_tile<GEMHOOK_UNROLL, (ILP > 0 ? ILP : 1)>(cells, nslots, lane, r);
+    if (ILP == 0) bin_add_tile_fwd<GEMHOOK_UNROLL, C>(cells, nslots, lane, r);
+    else bin_add_tile<GEMHOOK_UNROLL, (ILP > 0 ? ILP : 1), C>(cells, nslots, lane, r);
     // every lane has consumed its rows (the bin updates depend on them): the buffer may be overwritten
     __syncwarp();
     const u64 nt = t + (u64)stages * GW;
@@ -473,7 +484,7 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
       parity ^= 1u;
     }
     if (++since_flush >= flush_every) {
-      fold_bins(cells, acc, nslots, lane, true);
+      fold_bins<C>(cells, acc, nslots, lane, true);
       since_flush = 0;
     }
   }
@@ -482,11 +493,11 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
     for (int u = 0; u < GEMHOOK_UNROLL; u++) {
       const u64 i = full * tile + (unsigned)u * 32u + lane;
       const uint4 r = i < n ? ld_stream_16(rec + i) : make_uint4(0xffffffffu, 0u, 0u, 0u);
-      bin_add_tile<1>(cells, nslots, lane, &r);
+      bin_add_tile<1, 1, C>(cells, nslots, lane, &r);
     }
   }
-  fold_bins(cells, acc, nslots, lane, false);
-  block_epilogue(smem, nwarps, nslots, dev_totals, ticket, page, mm, dev_mem);
+  fold_bins<C>(cells, acc, nslots, lane, false);
+  block_epilogue<C>(smem, nwarps, nslots, dev_totals, ticket, page, mm, dev_mem);
 }
 
 extern "C" {
@@ -494,18 +505,20 @@ extern "C" {
 // With one warp per scheduler (four warps per SM at 64 slots) instruction latency is exposed: the group size of the bin
 // update (independent read-modify-write chains per lane) is what the per-warp rate depends on.  Variants by group size;
 // the host picks one (gh_acct.cpp).
-#define STAGED_KERNEL(NAME, ILP)                                                                                            \
+#define STAGED_KERNEL(NAME, ILP, C)                                                                                           \
   __global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 1)                                                    \
   NAME(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals, unsigned* __restrict__ ticket, \
        gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm, u64* __restrict__ dev_mem, unsigned flush_every,     \
        unsigned stages) {                                                                                                  \
-    reduce_staged_body<ILP>(rec, n, nslots, dev_totals, ticket, page, mm, dev_mem, flush_every, stages);                   \
+    reduce_staged_body<ILP, C>(rec, n, nslots, dev_totals, ticket, page, mm, dev_mem, flush_every, stages);                   \
   }
-STAGED_KERNEL(gemhook_acct_reduce_staged, 2)
-STAGED_KERNEL(gemhook_acct_reduce_staged_g4, 4)
-STAGED_KERNEL(gemhook_acct_reduce_staged_g8, 8)
-STAGED_KERNEL(gemhook_acct_reduce_staged_g1, 1)
-STAGED_KERNEL(gemhook_acct_reduce_staged_fwd, 0)
+STAGED_KERNEL(gemhook_acct_reduce_staged, 2, COLS)
+STAGED_KERNEL(gemhook_acct_reduce_staged_g4, 4, COLS)
+STAGED_KERNEL(gemhook_acct_reduce_staged_g8, 8, COLS)
+STAGED_KERNEL(gemhook_acct_reduce_staged_g1, 1, COLS)
+STAGED_KERNEL(gemhook_acct_reduce_staged_fwd, 0, COLS)
+STAGED_KERNEL(gemhook_acct_reduce_staged_fwd_c16, 0, 16u)
+STAGED_KERNEL(gemhook_acct_reduce_staged_g2_c16, 2, 16u)
 
 // The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight
 // warps, no shuffle trees, no ticket; the running totals come back from the atomics themselves, so nothing is re-read.

@@ -78,6 +78,7 @@ struct gemhook_acct {
   size_t ring_cap = 0;
   uint32_t nslots = 0;
   unsigned warps = 8, smem_bytes = 0, small_smem = 0, max_blocks = 0, flush_every = 8000;
+  unsigned staged_cols = 32;
   unsigned stages = 0;  // > 0: the TMA-staged kernel (many client slots) with this many 4 KB buffers per warp
   int sm_count = 0;
   mem_mirror mm = {0, 0, 0};
@@ -140,7 +141,12 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   const unsigned SMEM_MAX = 227u * 1024u, STG = TILE_RECORDS * 16u + 8u;
   bool staged = nslots > STAGED_MIN_SLOTS;
   if (const char* e = getenv("GEMHOOK_ACCT_STAGED")) staged = atoi(e) != 0;
+  unsigned per_warp_staged = per_warp;
+  if (const char* e = getenv("GEMHOOK_ACCT_STAGED_COLS")) {  // sweeps: 16-column bins (two lanes share a column, two phases)
+    if (atoi(e) == 16) a->staged_cols = 16, per_warp_staged = (nslots + 1u) * 16u * 16u + nslots * 24u;
+  }
   if (staged) {
+    const unsigned per_warp = per_warp_staged;  // (shadows the register-staged kernel's figure inside this block)
     unsigned best_w = 0, best_s = 0;
     for (unsigned w = 8; w >= 1 && !best_w; w--) {
       if (w * per_warp + 16u + w * 2u * STG > SMEM_MAX) continue;
@@ -175,6 +181,7 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
       if (atoi(e) == 1) name = "gemhook_acct_reduce_staged_g1";
       if (atoi(e) == 0) name = "gemhook_acct_reduce_staged_fwd";
     }
+    if (a->staged_cols == 16) name = strcmp(name, "gemhook_acct_reduce_staged") ? "gemhook_acct_reduce_staged_fwd_c16" : "gemhook_acct_reduce_staged_g2_c16";
     CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_staged, a->mod, name));
   }
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_small, a->mod, "gemhook_acct_reduce_small"));
@@ -186,7 +193,7 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
 
   a->nslots = nslots;
   a->smem_bytes = a->warps * per_warp;
-  if (a->stages) a->smem_bytes = ((a->smem_bytes + 15u) & ~15u) + a->warps * a->stages * STG;
+  if (a->stages) a->smem_bytes = ((a->warps * per_warp_staged + 15u) & ~15u) + a->warps * a->stages * STG;
   a->small_smem = (nslots + 1u) * GEMHOOK_COLS * 16u;
   CUfunction f_big = a->stages ? a->f_staged : a->f_reduce;
   if (a->smem_bytes > 48u * 1024u)

@@ -12,7 +12,7 @@ import kubeshare_b200 as kb
 torch.cuda.init()
 torch.zeros(1, device="cuda")
 PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6566.7
-KEYS = ("GEMHOOK_ACCT_WARPS", "GEMHOOK_ACCT_BLOCKS_PER_SM", "GEMHOOK_ACCT_SMALL", "GEMHOOK_ACCT_STAGED", "GEMHOOK_ACCT_STAGES", "GEMHOOK_ACCT_STAGED_ILP")
+KEYS = ("GEMHOOK_ACCT_WARPS", "GEMHOOK_ACCT_BLOCKS_PER_SM", "GEMHOOK_ACCT_SMALL", "GEMHOOK_ACCT_STAGED", "GEMHOOK_ACCT_STAGES", "GEMHOOK_ACCT_STAGED_ILP", "GEMHOOK_ACCT_STAGED_COLS")
 
 
 def records(n, nslots, seed=0):
@@ -47,14 +47,12 @@ def run(nslots, n, env=None, reps=8, check=None):
 
 
 big = 1 << 26
-for ns in (17, 24, 32, 48, 64):
-    ref = None
-    for ilp in (2, 1, 0, 4):
-        t = run(ns, big, {"GEMHOOK_ACCT_STAGED": "1", "GEMHOOK_ACCT_STAGED_ILP": str(ilp)}, check=ref)
-        ref = ref or t
-for w, st in ((4, 4), (5, 2), (3, 6)):
-    for ilp in (1, 0):
-        run(64, big, {"GEMHOOK_ACCT_STAGED": "1", "GEMHOOK_ACCT_STAGED_ILP": str(ilp), "GEMHOOK_ACCT_WARPS": str(w), "GEMHOOK_ACCT_STAGES": str(st)})
-for ilp in (1, 0):
-    run(16, big, {"GEMHOOK_ACCT_STAGED": "1", "GEMHOOK_ACCT_STAGED_ILP": str(ilp)})
-    run(8, big, {"GEMHOOK_ACCT_STAGED": "1", "GEMHOOK_ACCT_STAGED_ILP": str(ilp)})
+for ns in (32, 48, 64):
+    ref = run(ns, big, {"GEMHOOK_ACCT_STAGED": "1", "GEMHOOK_ACCT_STAGED_ILP": "0"})
+    for ilp in (0, 2):
+        for w in (8, 7, 6):
+            run(ns, big, {"GEMHOOK_ACCT_STAGED": "1", "GEMHOOK_ACCT_STAGED_ILP": str(ilp), "GEMHOOK_ACCT_STAGED_COLS": "16",
+                          "GEMHOOK_ACCT_WARPS": str(w)}, check=ref)
+for n in (513, 4097, (1 << 20) + 77):
+    ref = run(64, n, {"GEMHOOK_ACCT_STAGED": "0", "GEMHOOK_ACCT_SMALL": "0"}, reps=4)
+    run(64, n, {"GEMHOOK_ACCT_STAGED": "1", "GEMHOOK_ACCT_SMALL": "0", "GEMHOOK_ACCT_STAGED_ILP": "0", "GEMHOOK_ACCT_STAGED_COLS": "16"}, reps=4, check=ref)
