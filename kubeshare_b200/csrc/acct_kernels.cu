@@ -156,6 +156,8 @@ __device__ __forceinline__ void bin_add_group(uint4* cells, unsigned nslots, uns
 // U records of one lane, software-pipelined: the cell of record u+1 is loaded BEFORE the cell of record u is stored, so the
 // load latency of one record overlaps the adds of the previous one; if the two records name the same cell the loaded value
 // is stale and the value just computed is forwarded instead (one compare + four selects per record, no merging pass).
+// Measured in the TMA-staged kernel at 64 slots: merged groups of 2 / 4 / 8 records 0.865 / 0.880 / 0.643, one record at a
+// time 0.741, this 0.880 of the roofline -- and the best or equal at every other slot count.
 template <int U, unsigned C = COLS>
 __device__ __forceinline__ void bin_add_tile_fwd(uint4* cells, unsigned nslots, unsigned lane, const uint4* r) {
   unsigned off[U];
@@ -432,7 +434,7 @@ __device__ __forceinline__ void stage_wait(unsigned bar, unsigned parity) {
 
 }  // extern "C"
 
-template <int ILP, unsigned C>
+template <unsigned C>
 __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals,
                                                    unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page,
                                                    const gemhook_mem_mirror& mm, u64* __restrict__ dev_mem, unsigned flush_every,
@@ -473,8 +475,7 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
     const uint4* buf = reinterpret_cast<const uint4*>(stg_all + (size_t)(warp * stages + s) * STG_TILE_BYTES);
 #pragma unroll
     for (int u = 0; u < GEMHOOK_UNROLL; u++) r[u] = lds128(buf + (unsigned)u * 32u + lane);
-    if (ILP == 0) bin_add_tile_fwd<GEMHOOK_UNROLL, C>(cells, nslots, lane, r);
-    else bin_add_tile<GEMHOOK_UNROLL, (ILP > 0 ? ILP : 1), C>(cells, nslots, lane, r);
+    bin_add_tile_fwd<GEMHOOK_UNROLL, C>(cells, nslots, lane, r);
     // every lane has consumed its rows (the bin updates depend on them): the buffer may be overwritten
     __syncwarp();
     const u64 nt = t + (u64)stages * GW;
@@ -502,23 +503,19 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
 
 extern "C" {
 
-// With one warp per scheduler (four warps per SM at 64 slots) instruction latency is exposed: the group size of the bin
-// update (independent read-modify-write chains per lane) is what the per-warp rate depends on.  Variants by group size;
-// the host picks one (gh_acct.cpp).
-#define STAGED_KERNEL(NAME, ILP, C)                                                                                           \
+// Two instances: 32 columns (every lane its own) while eight warps with two buffers each still fit, 16 columns (lanes L and
+// L+16 share a column and take turns) beyond that -- half the bins, twice the warps.  With one warp per scheduler (four warps
+// per SM at 64 slots and 32 columns) instruction latency is exposed: 0.88 of the roofline; with 16 columns and eight warps
+// 0.95 (profiles/r02_acct_staged_variants.jsonl).  The host picks (gh_acct.cpp).
+#define STAGED_KERNEL(NAME, C)                                                                                              \
   __global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 1)                                                    \
   NAME(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals, unsigned* __restrict__ ticket, \
        gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm, u64* __restrict__ dev_mem, unsigned flush_every,     \
        unsigned stages) {                                                                                                  \
-    reduce_staged_body<ILP, C>(rec, n, nslots, dev_totals, ticket, page, mm, dev_mem, flush_every, stages);                   \
+    reduce_staged_body<C>(rec, n, nslots, dev_totals, ticket, page, mm, dev_mem, flush_every, stages);                     \
   }
-STAGED_KERNEL(gemhook_acct_reduce_staged, 2, COLS)
-STAGED_KERNEL(gemhook_acct_reduce_staged_g4, 4, COLS)
-STAGED_KERNEL(gemhook_acct_reduce_staged_g8, 8, COLS)
-STAGED_KERNEL(gemhook_acct_reduce_staged_g1, 1, COLS)
-STAGED_KERNEL(gemhook_acct_reduce_staged_fwd, 0, COLS)
-STAGED_KERNEL(gemhook_acct_reduce_staged_fwd_c16, 0, 16u)
-STAGED_KERNEL(gemhook_acct_reduce_staged_g2_c16, 2, 16u)
+STAGED_KERNEL(gemhook_acct_reduce_staged, 32u)
+STAGED_KERNEL(gemhook_acct_reduce_staged_c16, 16u)
 
 // The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight
 // warps, no shuffle trees, no ticket; the running totals come back from the atomics themselves, so nothing is re-read.

@@ -141,10 +141,14 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   const unsigned SMEM_MAX = 227u * 1024u, STG = TILE_RECORDS * 16u + 8u;
   bool staged = nslots > STAGED_MIN_SLOTS;
   if (const char* e = getenv("GEMHOOK_ACCT_STAGED")) staged = atoi(e) != 0;
+  // 32 columns while eight warps with two buffers each fit (up to 38 slots), 16 columns beyond: half the bins, twice the
+  // warps (measured at 48 / 64 slots: 0.99 / 0.88 of the roofline with 32 columns, 1.00 / 0.95 with 16)
   unsigned per_warp_staged = per_warp;
-  if (const char* e = getenv("GEMHOOK_ACCT_STAGED_COLS")) {  // sweeps: 16-column bins (two lanes share a column, two phases)
-    if (atoi(e) == 16) a->staged_cols = 16, per_warp_staged = (nslots + 1u) * 16u * 16u + nslots * 24u;
+  if (8u * (per_warp + 2u * STG) + 16u > SMEM_MAX) a->staged_cols = 16;
+  if (const char* e = getenv("GEMHOOK_ACCT_STAGED_COLS")) {  // sweeps
+    if (atoi(e) == 16 || atoi(e) == 32) a->staged_cols = (unsigned)atoi(e);
   }
+  if (a->staged_cols == 16) per_warp_staged = (nslots + 1u) * 16u * 16u + nslots * 24u;
   if (staged) {
     const unsigned per_warp = per_warp_staged;  // (shadows the register-staged kernel's figure inside this block)
     unsigned best_w = 0, best_s = 0;
@@ -173,17 +177,8 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
     }
   }
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, "gemhook_acct_reduce"));
-  {
-    const char* name = "gemhook_acct_reduce_staged";
-    if (const char* e = getenv("GEMHOOK_ACCT_STAGED_ILP")) {  // sweeps: group size of the bin update (2, 4, 8)
-      if (atoi(e) == 4) name = "gemhook_acct_reduce_staged_g4";
-      if (atoi(e) == 8) name = "gemhook_acct_reduce_staged_g8";
-      if (atoi(e) == 1) name = "gemhook_acct_reduce_staged_g1";
-      if (atoi(e) == 0) name = "gemhook_acct_reduce_staged_fwd";
-    }
-    if (a->staged_cols == 16) name = strcmp(name, "gemhook_acct_reduce_staged") ? "gemhook_acct_reduce_staged_fwd_c16" : "gemhook_acct_reduce_staged_g2_c16";
-    CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_staged, a->mod, name));
-  }
+  CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_staged, a->mod,
+                 a->staged_cols == 16 ? "gemhook_acct_reduce_staged_c16" : "gemhook_acct_reduce_staged"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_small, a->mod, "gemhook_acct_reduce_small"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_clear, a->mod, "gemhook_acct_clear"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_peek, a->mod, "gemhook_peek_pool"));

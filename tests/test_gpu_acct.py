@@ -136,19 +136,24 @@ def test_fast_path_boundary_and_equivalence(torch_cuda, OL, nslots, n, monkeypat
             a.close()
 
 
-@pytest.mark.parametrize("nslots,warps,stages", [(3, 8, 2), (17, 8, 3), (33, 6, 4), (64, 4, 5), (64, 5, 2), (64, 1, 8)])
+@pytest.mark.parametrize("nslots,warps,stages,cols", [(3, 8, 2, 32), (17, 8, 3, 32), (33, 6, 4, 32), (64, 4, 5, 32), (64, 1, 8, 32),
+                                                       (5, 8, 4, 16), (40, 8, 2, 16), (64, 8, 2, 16), (64, 3, 7, 16)])
 @pytest.mark.parametrize("n", [513, 767, 768, 769, 4096, 70_001, (1 << 21) + 255])
-def test_tma_staged_kernel_matches_oracle_and_the_register_staged_one(torch_cuda, OL, nslots, warps, stages, n, monkeypatch):
-    """gemhook_acct_reduce_staged (above 16 client slots by default): the same bins fed from per-warp rings of 4 KB
-    buffers filled with cp.async.bulk.  Forced on for small slot counts too, with ring depths 2..8, sizes that are not a
-    multiple of the 256-record tile, fewer tiles than warps, and the in-kernel flush every 2 tiles -- bit-exact against the
-    oracle, hence equal to the register-staged kernel."""
+def test_tma_staged_kernel_matches_oracle_and_the_register_staged_one(torch_cuda, OL, nslots, warps, stages, cols, n, monkeypatch):
+    """gemhook_acct_reduce_staged[_c16] (above 16 client slots by default; 16 columns above 38): the same bins fed from
+    per-warp rings of 4 KB buffers filled with cp.async.bulk, software-pipelined bin update with forwarding.  Forced on for
+    small slot counts too, both column counts, ring depths 2..8, sizes that are not a multiple of the 256-record tile, fewer
+    tiles than warps, the in-kernel flush every 2 tiles, runs of equal slots (forwarding) -- bit-exact against the oracle,
+    hence equal to the register-staged kernel."""
     monkeypatch.setenv("GEMHOOK_ACCT_SMALL", "0")
     monkeypatch.setenv("GEMHOOK_ACCT_FLUSH_EVERY", "2")
     r = make_records(n, nslots, seed=n + 31 * nslots + stages, big=True)
+    r["slot"][n // 3: n // 3 + 3000] = r["slot"][n // 3]          # a long run of one slot: every update forwards
+    r["slot"][n // 2: n // 2 + 4096: 2] = (nslots - 1)             # and an alternating pattern
     want = oracle(OL, r, nslots)
     for staged in ("1", "0"):
         monkeypatch.setenv("GEMHOOK_ACCT_STAGED", staged)
+        monkeypatch.setenv("GEMHOOK_ACCT_STAGED_COLS", str(cols))
         monkeypatch.setenv("GEMHOOK_ACCT_WARPS", str(warps))
         monkeypatch.setenv("GEMHOOK_ACCT_STAGES", str(stages))
         a = kb.Acct(nslots, ring_capacity=1 << 22)
