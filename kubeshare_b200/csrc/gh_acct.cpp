@@ -40,7 +40,7 @@ struct mem_mirror {  // mirrors gemhook_mem_mirror (kernel parameter, by value)
 #define GEMHOOK_UNROLL 8
 #endif
 const unsigned TILE_RECORDS = 32u * GEMHOOK_UNROLL;  // records per warp iteration (32 lanes x GEMHOOK_UNROLL)
-const unsigned STAGED_MIN_SLOTS = 16;                // above this many client slots the TMA-staged kernel runs (measured crossover)
+const unsigned STAGED_MIN_SLOTS = 20;                // above this many client slots the TMA-staged kernel runs (measured crossover)
 const size_t SMALL_N = 512;                          // up to here one warp does everything (gemhook_acct_reduce_small);
                                                      // measured: 10.5 vs 12.7 us at 2-64 records, break-even near 1024
 // shared memory per warp: (nslots + 1) rows of 32 16-byte cells (the extra row swallows out-of-range slots) + the
