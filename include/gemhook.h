@@ -252,6 +252,9 @@ uint64_t gemhook_acct_kernel_launches(const gemhook_acct *); /* our own kernels 
 uint64_t gemhook_acct_stream(const gemhook_acct *);           /* CUstream handle of the accounting stream */
 /* grid the kernel uses for n records (blocks), for the bench's roofline arithmetic (1 = the one-warp fast path) */
 uint32_t gemhook_acct_grid_for(const gemhook_acct *, size_t n);
+/* the launch shape chosen for this slot count: out = {warps per block, blocks in a full wave, dynamic shared memory in
+ * bytes, TMA buffers per warp (0: register-staged kernel), bin columns, shared memory of the one-warp kernel}. */
+void gemhook_acct_launch_shape(const gemhook_acct *, uint32_t out[6]);
 /* gpu_mem mirror (north_star b): the authoritative counter is the CAS word in the shared-pinned pool; (used, limit) of the
  * process's pod are handed to every reduce launch, whose publish step leaves them in device memory and in the totals
  * page.  read_mem: from_device = 0 reads the page (no CUDA call), 1 copies the device-resident words back. */

@@ -115,6 +115,7 @@ def lib():
         "gemhook_acct_sync": (C.c_int, [vp]), "gemhook_acct_reset": (C.c_int, [vp]),
         "gemhook_acct_kernel_launches": (u64, [vp]), "gemhook_acct_stream": (u64, [vp]),
         "gemhook_acct_grid_for": (u32, [vp, sz]),
+        "gemhook_acct_launch_shape": (None, [vp, C.POINTER(C.c_uint32)]),
         "gemhook_acct_set_mem": (None, [vp, u32, u64, u64]),
         "gemhook_acct_read_mem": (C.c_int, [vp, C.c_int, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "gemhook_acct_peek_host_words": (C.c_int, [vp, vp, C.POINTER(u64)]),
@@ -187,6 +188,11 @@ class Acct:
 
     def grid_for(self, n):
         return self.L.gemhook_acct_grid_for(self.h, n)
+
+    def launch_shape(self):
+        out = (C.c_uint32 * 6)()
+        self.L.gemhook_acct_launch_shape(self.h, out)
+        return dict(zip(("warps", "wave_blocks", "smem_bytes", "stages", "cols", "small_smem"), out))
 
     @property
     def kernel_launches(self):

@@ -141,7 +141,7 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   const unsigned SMEM_MAX = 227u * 1024u, STG = TILE_RECORDS * 16u + 8u;
   bool staged = nslots > STAGED_MIN_SLOTS;
   if (const char* e = getenv("GEMHOOK_ACCT_STAGED")) staged = atoi(e) != 0;
-  // 32 columns while eight warps with two buffers each fit (up to 38 slots), 16 columns beyond: half the bins, twice the
+  // 32 columns while eight warps with two buffers each fit (up to 37 slots), 16 columns beyond: half the bins, twice the
   // warps (measured at 48 / 64 slots: 0.99 / 0.88 of the roofline with 32 columns, 1.00 / 0.95 with 16)
   unsigned per_warp_staged = per_warp;
   if (8u * (per_warp + 2u * STG) + 16u > SMEM_MAX) a->staged_cols = 16;
@@ -241,6 +241,15 @@ GH_EXPORT void gemhook_acct_destroy(gemhook_acct* a) {
   if (a->stream) GH_CALL(cuStreamDestroy_v2, a->stream);
   if (a->mod) GH_CALL(cuModuleUnload, a->mod);
   delete a;
+}
+
+GH_EXPORT void gemhook_acct_launch_shape(const gemhook_acct* a, uint32_t out[6]) {
+  out[0] = a->warps;
+  out[1] = a->max_blocks;
+  out[2] = a->smem_bytes;
+  out[3] = a->stages;
+  out[4] = a->stages ? a->staged_cols : (unsigned)GEMHOOK_COLS;
+  out[5] = a->small_smem;
 }
 
 GH_EXPORT uint32_t gemhook_acct_grid_for(const gemhook_acct* a, size_t n) {

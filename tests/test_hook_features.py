@@ -4,6 +4,8 @@ device-reduced usage needs kernels that run: tests/test_gpu_hook.py.)"""
 import json
 import os
 import socket
+import subprocess as sp
+import sys
 import tempfile
 import threading
 
@@ -114,3 +116,42 @@ def test_failed_exchange_is_retried_on_the_same_socket():
     assert lim[0] == lim[1], "the swallowed REQ_MEM_LIMIT was not sent again"   # identical bytes, same req_id
     assert pm.raw[[r["type"] for r in reqs].index(wp.REQ_MEM_LIMIT)] == pm.raw[[r["type"] for r in reqs].index(wp.REQ_MEM_LIMIT) + 1]
     assert pm.connections == 1
+
+
+def test_accounting_kernel_launch_shapes_fit_the_sm_for_every_slot_count():
+    """gh_acct.cpp picks kernel, warps, ring depth and bin columns from the slot count.  On the CPU stub driver (any
+    cuModuleGetFunction succeeds) walk 1..64 slots and check the arithmetic: the block fits into 227 KB of shared memory,
+    the register-staged kernel runs up to 20 slots, the TMA-staged one beyond with >= 2 buffers per warp and >= 48 KB in
+    flight per SM, 16 columns once eight warps with 32 columns no longer fit."""
+    code = r"""
+import json, sys
+sys.path.insert(0, %r)
+import ctypes as C
+import kubeshare_b200 as kb
+cu = C.CDLL("libcuda.so.1")          # the stub driver (LD_LIBRARY_PATH): a context has to be current
+dev, ctx = C.c_int(), C.c_void_p()
+assert cu.cuInit(0) == 0 and cu.cuDeviceGet(C.byref(dev), 0) == 0 and cu.cuCtxCreate_v2(C.byref(ctx), 0, dev) == 0
+out = {}
+for ns in range(1, 65):
+    a = kb.Acct(ns, ring_capacity=1 << 10)
+    out[ns] = a.launch_shape()
+    a.close()
+print(json.dumps(out))
+""" % kb.ROOT
+    env = {k: v for k, v in os.environ.items() if not k.startswith("GEMHOOK_") and k != "LD_PRELOAD"}
+    env["LD_LIBRARY_PATH"] = kb.STUB_DIR + ":" + env.get("LD_LIBRARY_PATH", "")
+    p = sp.run([sys.executable, "-c", code], env=env, stdout=sp.PIPE, stderr=sp.PIPE, timeout=120)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    shapes = {int(k): v for k, v in json.loads(p.stdout.decode().strip().splitlines()[-1]).items()}
+    for ns, s in shapes.items():
+        assert s["smem_bytes"] <= 227 * 1024, (ns, s)
+        assert 1 <= s["warps"] <= 8 and s["wave_blocks"] >= 1
+        bins32 = (ns + 1) * 512 + ns * 24
+        if ns <= 20:
+            assert s["stages"] == 0 and s["cols"] == 32 and s["smem_bytes"] == s["warps"] * bins32, (ns, s)
+        else:
+            assert s["stages"] >= 2 and s["warps"] * s["stages"] * 4096 >= 48 * 1024, (ns, s)
+            assert s["cols"] == (32 if 8 * (bins32 + 2 * 4104) + 16 <= 227 * 1024 else 16), (ns, s)
+            per_warp = (ns + 1) * s["cols"] * 16 + ns * 24
+            assert s["smem_bytes"] == ((s["warps"] * per_warp + 15) & ~15) + s["warps"] * s["stages"] * 4104, (ns, s)
+    assert shapes[64] == dict(shapes[64], warps=8, stages=2, cols=16) and shapes[37]["cols"] == 32 and shapes[38]["cols"] == 16
