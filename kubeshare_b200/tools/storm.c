@@ -15,6 +15,11 @@
  *   graph    capture a CUDA graph on a non-blocking stream while hooked, replay it        (capture safety)
  *   probe    host cost of the primitives the hook builds on (launch, event record, elapsed, stamp)
  *
+ * Options shared by the co-residency modes: --start-barrier-dir DIR (all clients wait for each other after context creation,
+ * before the first call a hook could intercept); storm, mnist: --track-blocked (rdtsc around every launch; calls over 5 ms
+ * are token waits -> "blocked_s", so the client itself reports the time it really ran); storm: --pace-ns N (busy-wait after
+ * every launch: how a slower launcher looks to the driver's queue).
+ *
  * Output: ONE JSON object on stdout (or --out FILE).  Timing: CUDA events around the timed region on the
  * stream used (device time) AND CLOCK_MONOTONIC around the same region (host wall time).
  */
