@@ -34,7 +34,7 @@
 //     one system fence, then the epoch store;
 //   * gemhook_acct_reduce_small: one warp, no ticket, totals taken from the atomics' return values -- the live
 //     hook's regime (a flush carries tens of records) where fixed costs are everything;
-//   * gemhook_acct_reduce_staged[_c16] (above 20 client slots): the same bins fed from per-warp shared-memory rings that
+//   * gemhook_acct_reduce_staged[_c16] (above 22 client slots): the same bins fed from per-warp shared-memory rings that
 //     cp.async.bulk (TMA, mbarrier-tracked) keeps filled, software-pipelined bin update -- see the comment at the kernel.
 //
 // Build: nvcc -cubin -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (csrc/Makefile); the cubin

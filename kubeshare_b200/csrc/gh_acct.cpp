@@ -40,7 +40,7 @@ struct mem_mirror {  // mirrors gemhook_mem_mirror (kernel parameter, by value)
 #define GEMHOOK_UNROLL 8
 #endif
 const unsigned TILE_RECORDS = 32u * GEMHOOK_UNROLL;  // records per warp iteration (32 lanes x GEMHOOK_UNROLL)
-const unsigned STAGED_MIN_SLOTS = 20;                // above this many client slots the TMA-staged kernel runs (measured crossover)
+const unsigned STAGED_MIN_SLOTS = 22;                // above this many client slots the TMA-staged kernel runs (measured crossover)
 const size_t SMALL_N = 512;                          // up to here one warp does everything (gemhook_acct_reduce_small);
                                                      // measured: 10.5 vs 12.7 us at 2-64 records, break-even near 1024
 // shared memory per warp: (nslots + 1) rows of 32 16-byte cells (the extra row swallows out-of-range slots) + the
@@ -155,7 +155,7 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
     for (unsigned w = 8; w >= 1 && !best_w; w--) {
       if (w * per_warp + 16u + w * 2u * STG > SMEM_MAX) continue;
       unsigned s_ = (SMEM_MAX - w * per_warp - 16u) / (w * STG);
-      if (s_ > 8u) s_ = 8u;
+      if (s_ > 3u) s_ = 3u;  // measured at 20-22 slots, eight warps: 2 / 3 / 6 buffers -> 1.00 / 1.01 / 0.97 of the roofline
       if (w * s_ >= 12u || w == 1u) best_w = w, best_s = s_;
     }
     if (const char* e = getenv("GEMHOOK_ACCT_WARPS")) {

@@ -1,4 +1,4 @@
-"""Round 2, final kernel set: register-staged (<= 20 slots), TMA-staged with 32 columns (21-37), with 16 columns (38-64) as
+"""Round 2, final kernel set: register-staged (<= 22 slots), TMA-staged with 32 columns (23-37), with 16 columns (38-64) as
 the host selects them, by slot count.  One JSON object per line.   python profiles/scripts/r02_sweep_final2.py"""
 import os
 import sys

@@ -140,7 +140,7 @@ def test_fast_path_boundary_and_equivalence(torch_cuda, OL, nslots, n, monkeypat
                                                        (5, 8, 4, 16), (40, 8, 2, 16), (64, 8, 2, 16), (64, 3, 7, 16)])
 @pytest.mark.parametrize("n", [513, 767, 768, 769, 4096, 70_001, (1 << 21) + 255])
 def test_tma_staged_kernel_matches_oracle_and_the_register_staged_one(torch_cuda, OL, nslots, warps, stages, cols, n, monkeypatch):
-    """gemhook_acct_reduce_staged[_c16] (above 20 client slots by default; 16 columns above 37): the same bins fed from
+    """gemhook_acct_reduce_staged[_c16] (above 22 client slots by default; 16 columns above 37): the same bins fed from
     per-warp rings of 4 KB buffers filled with cp.async.bulk, software-pipelined bin update with forwarding.  Forced on for
     small slot counts too, both column counts, ring depths 2..8, sizes that are not a multiple of the 256-record tile, fewer
     tiles than warps, the in-kernel flush every 2 tiles, runs of equal slots (forwarding) -- bit-exact against the oracle,
