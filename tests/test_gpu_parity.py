@@ -226,7 +226,8 @@ def test_config5_four_client_mixed_fraction_ledger_matches_reference():
     comparable between the stacks; but in every stack (the reference included: 5547 ms next to 5413-5428) one client in a
     few runs is delivered 70-130 ms more than its peers for the same work -- the device made no progress for it while it
     held a token.  As in the storm test the client's own un-blocked run time tells the two apart: ledger time / un-blocked
-    time agrees within 1 % between the stacks, absolute time within 3 % per client and 1.5 % in total."""
+    time agrees within 1 % between the stacks (the strict assertion); absolute time within 5 % per client and 2.5 % in
+    total (the largest excursion seen in 14 runs: +2.7 % for one client, in the reference stack)."""
     res = _three_arms([0.1, 0.1, 0.4, 0.4], ["--mode", "mnist", "--iters", 400, "--track-blocked"])
     # Clients of one fraction class are interchangeable (first-token coin toss), so classes are compared sorted.
     ref = res["reference"]
@@ -234,12 +235,12 @@ def test_config5_four_client_mixed_fraction_ledger_matches_reference():
     for arm in ("ours-tcp", "pool"):
         got = res[arm]
         tot = sum(got["delivered_ms"].values())
-        assert abs(tot - tot_ref) <= 0.015 * tot_ref, (arm, tot, tot_ref)   # the same work holds the GPU equally long
+        assert abs(tot - tot_ref) <= 0.025 * tot_ref, (arm, tot, tot_ref)   # the same work holds the GPU equally long
         for cls in ((0, 1), (2, 3)):
             g = sorted(got["delivered_ms"][c] for c in cls)
             r = sorted(ref["delivered_ms"][c] for c in cls)
             for a, b in zip(g, r):
-                assert abs(a - b) <= 0.03 * b, (arm, cls, g, r)
+                assert abs(a - b) <= 0.05 * b, (arm, cls, g, r)
             gc = sorted(got["coverage"][c] for c in cls)
             rc = sorted(ref["coverage"][c] for c in cls)
             for a, b in zip(gc, rc):
