@@ -441,14 +441,14 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
                                                    unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page,
                                                    const gemhook_mem_mirror& mm, u64* __restrict__ dev_mem, unsigned flush_every,
                                                    unsigned stages) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(16) unsigned char smem_st[];  // (own name: C++ linkage here, C linkage in the kernels above)
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const unsigned nwarps = blockDim.x >> 5;
-  uint4* cells = reinterpret_cast<uint4*>(smem) + (size_t)warp * (nslots + 1u) * C;
-  u64* acc = reinterpret_cast<u64*>(smem + (size_t)nwarps * (nslots + 1u) * C * 16u) + (size_t)warp * nslots * 3u;
+  uint4* cells = reinterpret_cast<uint4*>(smem_st) + (size_t)warp * (nslots + 1u) * C;
+  u64* acc = reinterpret_cast<u64*>(smem_st + (size_t)nwarps * (nslots + 1u) * C * 16u) + (size_t)warp * nslots * 3u;
   const unsigned bins_bytes = nwarps * ((nslots + 1u) * C * 16u + nslots * 24u);
-  unsigned char* stg_all = smem + ((bins_bytes + 15u) & ~15u);  // (cp.async.bulk: 16-byte aligned destination)
+  unsigned char* stg_all = smem_st + ((bins_bytes + 15u) & ~15u);  // (cp.async.bulk: 16-byte aligned destination)
   const unsigned stg = smem_u32(stg_all) + warp * stages * STG_TILE_BYTES;
   const unsigned bars = smem_u32(stg_all) + nwarps * stages * STG_TILE_BYTES + warp * stages * 8u;
 
@@ -500,7 +500,7 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
     }
   }
   fold_bins<C>(cells, acc, nslots, lane, false);
-  block_epilogue<C>(smem, nwarps, nslots, dev_totals, ticket, page, mm, dev_mem);
+  block_epilogue<C>(smem_st, nwarps, nslots, dev_totals, ticket, page, mm, dev_mem);
 }
 
 extern "C" {
@@ -528,6 +528,19 @@ gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned ns
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned lane = threadIdx.x;
   uint4* cells = reinterpret_cast<uint4*>(smem);
+  // The kernel is alone on its stream and owns dev_totals, so the running totals are updated with plain loads and stores --
+  // and the loads are issued FIRST (through L2, where the big kernels' atomics were resolved), so their ~0.7 us round trip
+  // overlaps the record loads and the binning instead of following them as the return trip of an atomic.
+  const bool tree = nslots <= GEMHOOK_SHFL_SLOTS;  // few clients: warp tree, lane 0 owns every slot; else lane L owns L, L+32
+  const u64 e = __ldcg(dev_totals + nslots * 3u) + 1ull;
+  u64 old[GEMHOOK_SHFL_SLOTS * 3];
+#pragma unroll
+  for (unsigned k = 0; k < GEMHOOK_SHFL_SLOTS * 3u; k++) {
+    // tree: lane 0 needs totals 0 .. nslots*3-1; otherwise lane L needs those of slots L and L+32 (k = 0..5)
+    const unsigned t = tree ? k : (lane + (k / 3u) * 32u) * 3u + k % 3u;
+    const bool need = tree ? (lane == 0 && k < nslots * 3u) : (k < 6u && lane + (k / 3u) * 32u < nslots);
+    old[k] = need ? __ldcg(dev_totals + t) : 0ull;
+  }
   zero_bins(cells, nslots, lane);
   __syncwarp();
   // n <= 512 (host, gh_acct.cpp SMALL_N): a handful of records per lane, the packed count cannot overflow
@@ -541,32 +554,35 @@ gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned ns
     bin_add_tile<8>(cells, nslots, lane, r);
   }
   __syncwarp();
-  const u64 e = *reinterpret_cast<volatile u64*>(dev_totals + nslots * 3u) + 1ull;
   u64* dst = page ? page->buf[e & 1ull] : nullptr;
-  const bool tree = nslots <= GEMHOOK_SHFL_SLOTS;  // few clients: warp tree, lane 0 owns every slot
-  for (unsigned s = tree ? 0u : lane; s < nslots; s += tree ? 1u : 32u) {
+#pragma unroll
+  for (unsigned j = 0; j < GEMHOOK_SHFL_SLOTS; j++) {  // tree: slot j; otherwise slots lane, lane + 32 (j = 0, 1)
+    const unsigned s_ = tree ? j : lane + j * 32u;
+    if (s_ >= nslots || (!tree && j >= 2u)) continue;   // (uniform in tree mode)
     u64 ns = 0ull, la = 0ull, rc = 0ull;
     if (tree) {
-      warp_tree_slot(cells, s, lane, ns, la, rc);
+      warp_tree_slot(cells, s_, lane, ns, la, rc);
       if (lane != 0) continue;
     } else {
 #pragma unroll 8
       for (unsigned c = 0; c < COLS; c++) {
-        uint4 v = cells[s * COLS + ((c + lane) & (COLS - 1u))];
+        uint4 v = cells[s_ * COLS + ((c + lane) & (COLS - 1u))];
         u64 pk = ((u64)v.w << 32) | v.z;
         ns += ((u64)v.y << 32) | v.x;
         la += pk & PK_MASK;
         rc += pk >> 48;
       }
     }
-    // the kernel is alone on its stream and owns dev_totals: the values the atomics return ARE the old totals
-    u64 t0 = rc ? atomicAdd(dev_totals + s * 3u + 0u, ns) + ns : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 0u);
-    u64 t1 = rc ? atomicAdd(dev_totals + s * 3u + 1u, la) + la : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 1u);
-    u64 t2 = rc ? atomicAdd(dev_totals + s * 3u + 2u, rc) + rc : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 2u);
+    const u64 t0 = old[j * 3u + 0u] + ns, t1 = old[j * 3u + 1u] + la, t2 = old[j * 3u + 2u] + rc;
+    if (rc) {
+      __stcg(dev_totals + s_ * 3u + 0u, t0);
+      __stcg(dev_totals + s_ * 3u + 1u, t1);
+      __stcg(dev_totals + s_ * 3u + 2u, t2);
+    }
     if (dst) {
-      dst[s * 3u + 0u] = t0;
-      dst[s * 3u + 1u] = t1;
-      dst[s * 3u + 2u] = t2;
+      dst[s_ * 3u + 0u] = t0;
+      dst[s_ * 3u + 1u] = t1;
+      dst[s_ * 3u + 2u] = t2;
     }
   }
   if (lane == 0) {
