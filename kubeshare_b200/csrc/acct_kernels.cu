@@ -522,25 +522,14 @@ STAGED_KERNEL(gemhook_acct_reduce_staged_c16, 16u)
 // The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight
 // warps, no shuffle trees, no ticket; the running totals come back from the atomics themselves, so nothing is re-read.
 // dynamic shared memory: (nslots + 1) * COLS * 16 bytes.
+// (Tried: pre-loading the running totals through L2 at kernel start and updating them with plain stores instead of atomics
+//  with return -- 6.7-7.7 us under ncu against 5.8-6.4 us for this version on a box whose noop took 9 % longer: not kept.)
 __global__ void __launch_bounds__(32, 1)
 gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned nslots, u64* __restrict__ dev_totals,
                           gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm, u64* __restrict__ dev_mem) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned lane = threadIdx.x;
   uint4* cells = reinterpret_cast<uint4*>(smem);
-  // The kernel is alone on its stream and owns dev_totals, so the running totals are updated with plain loads and stores --
-  // and the loads are issued FIRST (through L2, where the big kernels' atomics were resolved), so their ~0.7 us round trip
-  // overlaps the record loads and the binning instead of following them as the return trip of an atomic.
-  const bool tree = nslots <= GEMHOOK_SHFL_SLOTS;  // few clients: warp tree, lane 0 owns every slot; else lane L owns L, L+32
-  const u64 e = __ldcg(dev_totals + nslots * 3u) + 1ull;
-  u64 old[GEMHOOK_SHFL_SLOTS * 3];
-#pragma unroll
-  for (unsigned k = 0; k < GEMHOOK_SHFL_SLOTS * 3u; k++) {
-    // tree: lane 0 needs totals 0 .. nslots*3-1; otherwise lane L needs those of slots L and L+32 (k = 0..5)
-    const unsigned t = tree ? k : (lane + (k / 3u) * 32u) * 3u + k % 3u;
-    const bool need = tree ? (lane == 0 && k < nslots * 3u) : (k < 6u && lane + (k / 3u) * 32u < nslots);
-    old[k] = need ? __ldcg(dev_totals + t) : 0ull;
-  }
   zero_bins(cells, nslots, lane);
   __syncwarp();
   // n <= 512 (host, gh_acct.cpp SMALL_N): a handful of records per lane, the packed count cannot overflow
@@ -554,35 +543,32 @@ gemhook_acct_reduce_small(const uint4* __restrict__ rec, unsigned n, unsigned ns
     bin_add_tile<8>(cells, nslots, lane, r);
   }
   __syncwarp();
+  const u64 e = *reinterpret_cast<volatile u64*>(dev_totals + nslots * 3u) + 1ull;
   u64* dst = page ? page->buf[e & 1ull] : nullptr;
-#pragma unroll
-  for (unsigned j = 0; j < GEMHOOK_SHFL_SLOTS; j++) {  // tree: slot j; otherwise slots lane, lane + 32 (j = 0, 1)
-    const unsigned s_ = tree ? j : lane + j * 32u;
-    if (s_ >= nslots || (!tree && j >= 2u)) continue;   // (uniform in tree mode)
+  const bool tree = nslots <= GEMHOOK_SHFL_SLOTS;  // few clients: warp tree, lane 0 owns every slot
+  for (unsigned s = tree ? 0u : lane; s < nslots; s += tree ? 1u : 32u) {
     u64 ns = 0ull, la = 0ull, rc = 0ull;
     if (tree) {
-      warp_tree_slot(cells, s_, lane, ns, la, rc);
+      warp_tree_slot(cells, s, lane, ns, la, rc);
       if (lane != 0) continue;
     } else {
 #pragma unroll 8
       for (unsigned c = 0; c < COLS; c++) {
-        uint4 v = cells[s_ * COLS + ((c + lane) & (COLS - 1u))];
+        uint4 v = cells[s * COLS + ((c + lane) & (COLS - 1u))];
         u64 pk = ((u64)v.w << 32) | v.z;
         ns += ((u64)v.y << 32) | v.x;
         la += pk & PK_MASK;
         rc += pk >> 48;
       }
     }
-    const u64 t0 = old[j * 3u + 0u] + ns, t1 = old[j * 3u + 1u] + la, t2 = old[j * 3u + 2u] + rc;
-    if (rc) {
-      __stcg(dev_totals + s_ * 3u + 0u, t0);
-      __stcg(dev_totals + s_ * 3u + 1u, t1);
-      __stcg(dev_totals + s_ * 3u + 2u, t2);
-    }
+    // the kernel is alone on its stream and owns dev_totals: the values the atomics return ARE the old totals
+    u64 t0 = rc ? atomicAdd(dev_totals + s * 3u + 0u, ns) + ns : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 0u);
+    u64 t1 = rc ? atomicAdd(dev_totals + s * 3u + 1u, la) + la : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 1u);
+    u64 t2 = rc ? atomicAdd(dev_totals + s * 3u + 2u, rc) + rc : *reinterpret_cast<volatile u64*>(dev_totals + s * 3u + 2u);
     if (dst) {
-      dst[s_ * 3u + 0u] = t0;
-      dst[s_ * 3u + 1u] = t1;
-      dst[s_ * 3u + 2u] = t2;
+      dst[s * 3u + 0u] = t0;
+      dst[s * 3u + 1u] = t1;
+      dst[s * 3u + 2u] = t2;
     }
   }
   if (lane == 0) {
