@@ -360,12 +360,18 @@ def jain(xs):
 
 
 def fairness(run):
-    """Jain's index of delivered/entitled GPU time: delivered = ledger ms (token time) when the arm has a ledger,
-    else the client's completion rate; entitled = its min-fraction."""
-    if run.get("ledger_ms") and all(v is not None for v in run["ledger_ms"]) and sum(run["ledger_ms"]) > 0:
-        return jain([d / f for d, f in zip(run["ledger_ms"], run["fracs"])]), "ledger_ms/min_fraction"
+    """Jain's index of rate/entitlement, the same basis in both arms: rate = the client's completion rate (launches per
+    second of its own wall time), entitlement = its min-fraction.  (The ledger share is no basis for a fixed-work run: every
+    client needs the same token time for the same work, whatever its fraction -- 0.735 by construction for
+    0.1/0.1/0.4/0.4; it is reported next to it where the arm has a ledger.)"""
     return jain([l / w / f for l, w, f in zip(run["per_client_launches"], run["per_client_wall_s"], run["fracs"])]), \
         "completion_rate/min_fraction"
+
+
+def fairness_ledger(run):
+    if run.get("ledger_ms") and all(v is not None for v in run["ledger_ms"]) and sum(run["ledger_ms"]) > 0:
+        return round(jain([d / f for d, f in zip(run["ledger_ms"], run["fracs"])]), 4)
+    return None
 
 
 # --------------------------------------------------------------------------------------------- roofline
@@ -562,7 +568,7 @@ def main():
                     "unhooked_launches_per_s": round(un_o["launches_per_s_device"], 1),
                     "hooked_launches_per_s": round(hk_o["launches_per_s_device"], 1),
                     "overhead_pct": round((un_o["launches_per_s_device"] / hk_o["launches_per_s_device"] - 1.0) * 100.0, 3),
-                    "jain_fairness": round(jf, 4), "fairness_of": how}
+                    "jain_fairness": round(jf, 4), "fairness_of": how, "jain_ledger_share": fairness_ledger(hk_o)}
             except Exception as e:  # noqa: BLE001 -- a side sample must not take the headline down
                 log("%s sample failed: %r" % (wl, e))
 
@@ -668,7 +674,7 @@ def main():
     else:
         jf, how = fairness(head_runs[0])
         line["unhooked_launches_per_s"] = sweep_out[str(hc)]["unhooked_launches_per_s"]
-        line["jain_fairness"] = {"value": round(jf, 5), "of": how}
+        line["jain_fairness"] = {"value": round(jf, 5), "of": how, "ledger_share": fairness_ledger(head_runs[0])}
     if head_runs[0].get("ledger_ms"):
         line["ledger_ms"] = [round(v, 3) for v in head_runs[0]["ledger_ms"]]
     if head_runs[0].get("ledger_gaps"):

@@ -38,5 +38,6 @@ def test_two_replicas_aggregate():
         assert set(line["clients"]) == {"1", "2"}
     assert (one["n_gpus"], two["n_gpus"]) == (1, 2)
     # two independent replicas process twice the launches in about the same time
-    assert 1.4 < two["value"] / one["value"] < 2.6
+    # summed over replicas, not the slower one's alone (that would read ~1.0); wide: eight shared CPU cores run both replicas
+    assert 1.15 < two["value"] / one["value"] < 3.2
     assert two["config"]["parallelism"].startswith("replicas x2")
