@@ -413,12 +413,13 @@ gemhook_acct_reduce(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* 
 // not by the register file, and four warps are enough for the arithmetic (one 32-record row per ~90 cycles per warp).
 // dynamic shared memory: bins + accumulators of the warps as above, then (16-byte aligned) warps x stages x 4096 bytes of
 // staging and warps x stages mbarriers.
-#define STG_TILE_BYTES (32u * GEMHOOK_UNROLL * 16u)
+// bytes per ring buffer: R rows of 32 records (R = GEMHOOK_UNROLL = 8 -> 4 KB; 4 -> 2 KB where shared memory is tightest)
+#define STG_BYTES(R) (32u * (unsigned)(R) * 16u)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void stage_fill(unsigned dst, const uint4* src, unsigned bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(STG_TILE_BYTES) : "memory");
+__device__ __forceinline__ void stage_fill(unsigned dst, const uint4* src, unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(STG_TILE_BYTES), "r"(bar)
+               "r"(bytes), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void stage_wait(unsigned bar, unsigned parity) {
@@ -436,7 +437,7 @@ __device__ __forceinline__ void stage_wait(unsigned bar, unsigned parity) {
 
 }  // extern "C"
 
-template <unsigned C>
+template <unsigned C, int R>
 __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals,
                                                    unsigned* __restrict__ ticket, gemhook_totals_page* __restrict__ page,
                                                    const gemhook_mem_mirror& mm, u64* __restrict__ dev_mem, unsigned flush_every,
@@ -449,8 +450,8 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
   u64* acc = reinterpret_cast<u64*>(smem_st + (size_t)nwarps * (nslots + 1u) * C * 16u) + (size_t)warp * nslots * 3u;
   const unsigned bins_bytes = nwarps * ((nslots + 1u) * C * 16u + nslots * 24u);
   unsigned char* stg_all = smem_st + ((bins_bytes + 15u) & ~15u);  // (cp.async.bulk: 16-byte aligned destination)
-  const unsigned stg = smem_u32(stg_all) + warp * stages * STG_TILE_BYTES;
-  const unsigned bars = smem_u32(stg_all) + nwarps * stages * STG_TILE_BYTES + warp * stages * 8u;
+  const unsigned stg = smem_u32(stg_all) + warp * stages * STG_BYTES(R);
+  const unsigned bars = smem_u32(stg_all) + nwarps * stages * STG_BYTES(R) + warp * stages * 8u;
 
   zero_bins<C>(cells, nslots, lane);
   for (unsigned t = lane; t < nslots * 3u; t += 32u) acc[t] = 0ull;
@@ -460,28 +461,28 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
   }
   __syncwarp();
 
-  const u64 tile = 32ull * GEMHOOK_UNROLL;  // records per stage
+  const u64 tile = 32ull * R;  // records per buffer
   const u64 full = n / tile;                // whole tiles: bulk copies; the ragged rest goes through plain loads below
   const u64 gw = (u64)blockIdx.x * nwarps + warp, GW = (u64)gridDim.x * nwarps;
   // this warp's k-th tile is tile gw + k * GW; its buffer is k % stages, used for the (k / stages)-th time
   if (lane == 0) {
     for (unsigned k = 0; k < stages; k++) {
       const u64 t = gw + (u64)k * GW;
-      if (t < full) stage_fill(stg + k * STG_TILE_BYTES, rec + t * tile, bars + k * 8u);
+      if (t < full) stage_fill(stg + k * STG_BYTES(R), rec + t * tile, bars + k * 8u, STG_BYTES(R));
     }
   }
   unsigned since_flush = 0, s = 0, parity = 0;
   for (u64 t = gw; t < full; t += GW) {
     stage_wait(bars + s * 8u, parity);
-    uint4 r[GEMHOOK_UNROLL];
-    const uint4* buf = reinterpret_cast<const uint4*>(stg_all + (size_t)(warp * stages + s) * STG_TILE_BYTES);
+    uint4 r[R];
+    const uint4* buf = reinterpret_cast<const uint4*>(stg_all + (size_t)(warp * stages + s) * STG_BYTES(R));
 #pragma unroll
-    for (int u = 0; u < GEMHOOK_UNROLL; u++) r[u] = lds128(buf + (unsigned)u * 32u + lane);
-    bin_add_tile_fwd<GEMHOOK_UNROLL, C>(cells, nslots, lane, r);
+    for (int u = 0; u < R; u++) r[u] = lds128(buf + (unsigned)u * 32u + lane);
+    bin_add_tile_fwd<R, C>(cells, nslots, lane, r);
     // every lane has consumed its rows (the bin updates depend on them): the buffer may be overwritten
     __syncwarp();
     const u64 nt = t + (u64)stages * GW;
-    if (lane == 0 && nt < full) stage_fill(stg + s * STG_TILE_BYTES, rec + nt * tile, bars + s * 8u);
+    if (lane == 0 && nt < full) stage_fill(stg + s * STG_BYTES(R), rec + nt * tile, bars + s * 8u, STG_BYTES(R));
     if (++s == stages) {
       s = 0;
       parity ^= 1u;
@@ -493,7 +494,7 @@ __device__ __forceinline__ void reduce_staged_body(const uint4* __restrict__ rec
   }
   if (gw == full % GW) {  // ragged tail of the ring (< one tile): the warp whose turn it would be
 #pragma unroll 1
-    for (int u = 0; u < GEMHOOK_UNROLL; u++) {
+    for (int u = 0; u < R; u++) {
       const u64 i = full * tile + (unsigned)u * 32u + lane;
       const uint4 r = i < n ? ld_stream_16(rec + i) : make_uint4(0xffffffffu, 0u, 0u, 0u);
       bin_add_tile<1, 1, C>(cells, nslots, lane, &r);
@@ -509,15 +510,17 @@ extern "C" {
 // L+16 share a column and take turns) beyond that -- half the bins, twice the warps.  With one warp per scheduler (four warps
 // per SM at 64 slots and 32 columns) instruction latency is exposed: 0.88 of the roofline; with 16 columns and eight warps
 // 0.95 (profiles/r02_acct_staged_variants.jsonl).  The host picks (gh_acct.cpp).
-#define STAGED_KERNEL(NAME, C)                                                                                              \
-  __global__ void __launch_bounds__(GEMHOOK_MAX_WARPS_PER_BLOCK * 32, 1)                                                    \
+#define STAGED_KERNEL(NAME, C, R, MAXW)                                                                                     \
+  __global__ void __launch_bounds__((MAXW) * 32, 1)                                                                         \
   NAME(const uint4* __restrict__ rec, u64 n, unsigned nslots, u64* __restrict__ dev_totals, unsigned* __restrict__ ticket, \
        gemhook_totals_page* __restrict__ page, gemhook_mem_mirror mm, u64* __restrict__ dev_mem, unsigned flush_every,     \
        unsigned stages) {                                                                                                  \
-    reduce_staged_body<C>(rec, n, nslots, dev_totals, ticket, page, mm, dev_mem, flush_every, stages);                     \
+    reduce_staged_body<C, R>(rec, n, nslots, dev_totals, ticket, page, mm, dev_mem, flush_every, stages);                  \
   }
-STAGED_KERNEL(gemhook_acct_reduce_staged, 32u)
-STAGED_KERNEL(gemhook_acct_reduce_staged_c16, 16u)
+STAGED_KERNEL(gemhook_acct_reduce_staged, 32u, GEMHOOK_UNROLL, GEMHOOK_MAX_WARPS_PER_BLOCK)
+STAGED_KERNEL(gemhook_acct_reduce_staged_c16, 16u, GEMHOOK_UNROLL, GEMHOOK_MAX_WARPS_PER_BLOCK)
+// sweep: 2 KB buffers and up to twelve warps per block (16 columns), for the fullest slot tables
+STAGED_KERNEL(gemhook_acct_reduce_staged_c16_r4, 16u, 4, 12)
 
 // The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight
 // warps, no shuffle trees, no ticket; the running totals come back from the atomics themselves, so nothing is re-read.

@@ -79,6 +79,7 @@ struct gemhook_acct {
   uint32_t nslots = 0;
   unsigned warps = 8, smem_bytes = 0, small_smem = 0, max_blocks = 0, flush_every = 8000;
   unsigned staged_cols = 32;
+  unsigned stage_rows = GEMHOOK_UNROLL;  // 32-record rows per ring buffer (8 -> 4 KB); 4 with GEMHOOK_ACCT_STAGE_ROWS=4 (sweeps)
   unsigned stages = 0;  // > 0: the TMA-staged kernel (many client slots) with this many 4 KB buffers per warp
   int sm_count = 0;
   mem_mirror mm = {0, 0, 0};
@@ -138,21 +139,25 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   // HBM busy.  gemhook_acct_reduce_staged feeds the same accumulation from per-warp rings of 4 KB buffers filled by
   // cp.async.bulk, so the bytes in flight are set by the ring: pick the largest warp count (one block per SM) that still
   // leaves every warp >= 2 buffers and the SM >= 48 KB in flight (the HBM latency x bandwidth product is ~36 KB per SM).
-  const unsigned SMEM_MAX = 227u * 1024u, STG = TILE_RECORDS * 16u + 8u;
+  unsigned max_warps = 8;
+  if (const char* e = getenv("GEMHOOK_ACCT_STAGE_ROWS")) {  // sweeps: 2 KB buffers, up to twelve warps (16 columns only)
+    if (atoi(e) == 4) a->stage_rows = 4, max_warps = 12;
+  }
+  const unsigned SMEM_MAX = 227u * 1024u, STG = 32u * a->stage_rows * 16u + 8u;
   bool staged = nslots > STAGED_MIN_SLOTS;
   if (const char* e = getenv("GEMHOOK_ACCT_STAGED")) staged = atoi(e) != 0;
   // 32 columns while eight warps with two buffers each fit (up to 37 slots), 16 columns beyond: half the bins, twice the
   // warps (measured at 48 / 64 slots: 0.99 / 0.88 of the roofline with 32 columns, 1.00 / 0.95 with 16)
   unsigned per_warp_staged = per_warp;
-  if (8u * (per_warp + 2u * STG) + 16u > SMEM_MAX) a->staged_cols = 16;
+  if (8u * (per_warp + 2u * STG) + 16u > SMEM_MAX || a->stage_rows == 4) a->staged_cols = 16;
   if (const char* e = getenv("GEMHOOK_ACCT_STAGED_COLS")) {  // sweeps
-    if (atoi(e) == 16 || atoi(e) == 32) a->staged_cols = (unsigned)atoi(e);
+    if ((atoi(e) == 16 || atoi(e) == 32) && a->stage_rows != 4) a->staged_cols = (unsigned)atoi(e);
   }
   if (a->staged_cols == 16) per_warp_staged = (nslots + 1u) * 16u * 16u + nslots * 24u;
   if (staged) {
     const unsigned per_warp = per_warp_staged;  // (shadows the register-staged kernel's figure inside this block)
     unsigned best_w = 0, best_s = 0;
-    for (unsigned w = 8; w >= 1 && !best_w; w--) {
+    for (unsigned w = max_warps; w >= 1 && !best_w; w--) {
       if (w * per_warp + 16u + w * 2u * STG > SMEM_MAX) continue;
       unsigned s_ = (SMEM_MAX - w * per_warp - 16u) / (w * STG);
       if (s_ > 3u) s_ = 3u;  // measured at 20-22 slots, eight warps: 2 / 3 / 6 buffers -> 1.00 / 1.01 / 0.97 of the roofline
@@ -160,7 +165,7 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
     }
     if (const char* e = getenv("GEMHOOK_ACCT_WARPS")) {
       unsigned w = (unsigned)atoi(e);
-      if (w >= 1u && w <= 8u && w * per_warp + 16u + w * 2u * STG <= SMEM_MAX) {
+      if (w >= 1u && w <= max_warps && w * per_warp + 16u + w * 2u * STG <= SMEM_MAX) {
         best_w = w;
         best_s = (SMEM_MAX - w * per_warp - 16u) / (w * STG);
         if (best_s > 8u) best_s = 8u;
@@ -178,7 +183,8 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   }
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, "gemhook_acct_reduce"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_staged, a->mod,
-                 a->staged_cols == 16 ? "gemhook_acct_reduce_staged_c16" : "gemhook_acct_reduce_staged"));
+                 a->stage_rows == 4 ? "gemhook_acct_reduce_staged_c16_r4"
+                                    : a->staged_cols == 16 ? "gemhook_acct_reduce_staged_c16" : "gemhook_acct_reduce_staged"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_small, a->mod, "gemhook_acct_reduce_small"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_clear, a->mod, "gemhook_acct_clear"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_peek, a->mod, "gemhook_peek_pool"));
@@ -254,7 +260,7 @@ GH_EXPORT void gemhook_acct_launch_shape(const gemhook_acct* a, uint32_t out[6])
 
 GH_EXPORT uint32_t gemhook_acct_grid_for(const gemhook_acct* a, size_t n) {
   if (a->small_enabled && n <= SMALL_N) return 1;
-  size_t per_block = (size_t)a->warps * TILE_RECORDS;
+  size_t per_block = (size_t)a->warps * (a->stages ? 32u * a->stage_rows : TILE_RECORDS);
   size_t want = (n + per_block - 1) / per_block;
   if (want < 1) want = 1;
   if (want > a->max_blocks) want = a->max_blocks;
