@@ -519,8 +519,8 @@ extern "C" {
   }
 STAGED_KERNEL(gemhook_acct_reduce_staged, 32u, GEMHOOK_UNROLL, GEMHOOK_MAX_WARPS_PER_BLOCK)
 STAGED_KERNEL(gemhook_acct_reduce_staged_c16, 16u, GEMHOOK_UNROLL, GEMHOOK_MAX_WARPS_PER_BLOCK)
-// sweep: 2 KB buffers and up to twelve warps per block (16 columns), for the fullest slot tables
-STAGED_KERNEL(gemhook_acct_reduce_staged_c16_r4, 16u, 4, 12)
+// (2 KB buffers -- R = 4 -- with nine or ten warps per SM were measured too: 0.80-0.82 of the roofline at 48-64 slots against
+//  0.95-1.00 for 4 KB buffers and eight warps; the per-buffer costs -- barrier wait, copy issue -- double.)
 
 // The live hook's regime: a flush carries a handful to a few thousand records.  ONE warp: no bin zeroing for eight
 // warps, no shuffle trees, no ticket; the running totals come back from the atomics themselves, so nothing is re-read.

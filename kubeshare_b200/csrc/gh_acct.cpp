@@ -79,7 +79,7 @@ struct gemhook_acct {
   uint32_t nslots = 0;
   unsigned warps = 8, smem_bytes = 0, small_smem = 0, max_blocks = 0, flush_every = 8000;
   unsigned staged_cols = 32;
-  unsigned stage_rows = GEMHOOK_UNROLL;  // 32-record rows per ring buffer (8 -> 4 KB); 4 with GEMHOOK_ACCT_STAGE_ROWS=4 (sweeps)
+  const unsigned stage_rows = GEMHOOK_UNROLL;  // 32-record rows per ring buffer (8 -> 4 KB; 2 KB buffers measured slower)
   unsigned stages = 0;  // > 0: the TMA-staged kernel (many client slots) with this many 4 KB buffers per warp
   int sm_count = 0;
   mem_mirror mm = {0, 0, 0};
@@ -139,19 +139,16 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   // HBM busy.  gemhook_acct_reduce_staged feeds the same accumulation from per-warp rings of 4 KB buffers filled by
   // cp.async.bulk, so the bytes in flight are set by the ring: pick the largest warp count (one block per SM) that still
   // leaves every warp >= 2 buffers and the SM >= 48 KB in flight (the HBM latency x bandwidth product is ~36 KB per SM).
-  unsigned max_warps = 8;
-  if (const char* e = getenv("GEMHOOK_ACCT_STAGE_ROWS")) {  // sweeps: 2 KB buffers, up to twelve warps (16 columns only)
-    if (atoi(e) == 4) a->stage_rows = 4, max_warps = 12;
-  }
+  const unsigned max_warps = 8;
   const unsigned SMEM_MAX = 227u * 1024u, STG = 32u * a->stage_rows * 16u + 8u;
   bool staged = nslots > STAGED_MIN_SLOTS;
   if (const char* e = getenv("GEMHOOK_ACCT_STAGED")) staged = atoi(e) != 0;
   // 32 columns while eight warps with two buffers each fit (up to 37 slots), 16 columns beyond: half the bins, twice the
   // warps (measured at 48 / 64 slots: 0.99 / 0.88 of the roofline with 32 columns, 1.00 / 0.95 with 16)
   unsigned per_warp_staged = per_warp;
-  if (8u * (per_warp + 2u * STG) + 16u > SMEM_MAX || a->stage_rows == 4) a->staged_cols = 16;
+  if (8u * (per_warp + 2u * STG) + 16u > SMEM_MAX) a->staged_cols = 16;
   if (const char* e = getenv("GEMHOOK_ACCT_STAGED_COLS")) {  // sweeps
-    if ((atoi(e) == 16 || atoi(e) == 32) && a->stage_rows != 4) a->staged_cols = (unsigned)atoi(e);
+    if (atoi(e) == 16 || atoi(e) == 32) a->staged_cols = (unsigned)atoi(e);
   }
   if (a->staged_cols == 16) per_warp_staged = (nslots + 1u) * 16u * 16u + nslots * 24u;
   if (staged) {
@@ -183,8 +180,7 @@ static int acct_init(gemhook_acct* a, uint32_t nslots, size_t ring_cap) {
   }
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_reduce, a->mod, "gemhook_acct_reduce"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_staged, a->mod,
-                 a->stage_rows == 4 ? "gemhook_acct_reduce_staged_c16_r4"
-                                    : a->staged_cols == 16 ? "gemhook_acct_reduce_staged_c16" : "gemhook_acct_reduce_staged"));
+                 a->staged_cols == 16 ? "gemhook_acct_reduce_staged_c16" : "gemhook_acct_reduce_staged"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_small, a->mod, "gemhook_acct_reduce_small"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_clear, a->mod, "gemhook_acct_clear"));
   CU_TRY(GH_CALL(cuModuleGetFunction, &a->f_peek, a->mod, "gemhook_peek_pool"));
