@@ -1,5 +1,5 @@
-"""Round 2: 2 KB ring buffers and more than eight warps per SM (16 columns) at the fullest slot tables.
-   python profiles/scripts/r02_sweep_rows4.py"""
+"""Round 2: 2 KB ring buffers and more than eight warps per SM (16 columns) at the fullest slot tables -- the variant this script
+   drove (GEMHOOK_ACCT_STAGE_ROWS=4) was removed after the measurement: profiles/r02_acct_staged_variants.jsonl, last 21 rows."""
 import os
 import sys
 src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "r02_sweep_staged.py")).read()
