@@ -180,3 +180,28 @@ def test_racing_clients_reload_a_quota_file_version_exactly_once():
             assert lim.value == 10 + round_
         for h in handles:
             L.gemhook_pool_close(h)
+
+
+def test_pool_clock_places_ledger_entries_on_the_readers_clock():
+    """gemhook_pool_now_ms is the ledger's time base (ms since the pool was created, CLOCK_MONOTONIC -- gem-schd's
+    ms_since_start, scheduler.cpp:107-109): a reader that notes its own monotonic clock next to it can tell when a ledger entry
+    began and ended.  Two handles on one file read the same clock."""
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "pool").encode()
+        p = L.gemhook_pool_open(path, 1, 300.0, 20.0, 10000.0, 0)
+        q = L.gemhook_pool_open(path, 0, 0, 0, 0, 0)              # an observer on the same file
+        assert L.gemhook_pool_load_config(p, b"1\nns/a 1.0 1.0 1000\n", 0) == 1
+        t0 = time.monotonic() - L.gemhook_pool_now_ms(p) / 1e3   # the pool's origin on this process's clock
+        a, b = L.gemhook_pool_now_ms(p), L.gemhook_pool_now_ms(q)
+        assert 0.0 <= a <= b <= a + 50.0
+        before = (time.monotonic() - t0) * 1e3
+        quota = L.gemhook_pool_acquire(p, 0, 0.0, 0.0)
+        after = (time.monotonic() - t0) * 1e3
+        assert quota > 0
+        n = L.gemhook_pool_history(q, None, None, None, 0)
+        sl, s, e = (C.c_int * n)(), (C.c_double * n)(), (C.c_double * n)()
+        L.gemhook_pool_history(q, sl, s, e, n)
+        assert n == 1 and before - 1.0 <= s[0] <= after + 1.0, (before, s[0], after)   # granted between the two stamps
+        assert e[0] == s[0] + quota                                                     # Record(): end = start + quota
+        L.gemhook_pool_close(q)
+        L.gemhook_pool_close(p)
